@@ -1,0 +1,165 @@
+/*
+ * sdb200 — C ABI of the B200-native latent-diffusion kernels.
+ *
+ * The reference (CompVis/stable-diffusion) has no FFI: its plug-in boundary is `instantiate_from_config`
+ * (ldm/util.py:78-93) plus the duck-typed nn.Module contracts around the denoising loop. This header is the
+ * boundary a maintainer binds instead (ctypes stub in INTEGRATION.md): plain pointers and sizes, no torch
+ * types. Every entry point enqueues work on `stream` and returns immediately; 0 = OK, non-zero = error
+ * (text via sdb_last_error()). All device pointers are owned by the caller.
+ *
+ * Each function cites the reference operation(s) it replaces.
+ */
+#ifndef SDB200_H
+#define SDB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* sdb_stream_t; /* cudaStream_t */
+
+const char* sdb_last_error(void);
+int sdb_version(void);
+int sdb_sm_count(void);
+
+/* ---- epilogue activations ---- */
+enum {
+  SDB_ACT_NONE = 0,
+  SDB_ACT_GEGLU = 1,      /* out[:, j] = x_j * gelu_erf(gate_j); ldm/modules/attention.py:37-45 (weights packed
+                             so each accumulator tile holds [x half | gate half]) */
+  SDB_ACT_QUICK_GELU = 2, /* x * sigmoid(1.702 x): CLIP MLP (transformers CLIPMLP, quick_gelu) */
+  SDB_ACT_SILU = 3        /* x * sigmoid(x): time_embed MLP, openaimodel.py:506-511 */
+};
+
+/*
+ * Tensor-core GEMM / implicit-GEMM convolution (tcgen05 + TMA), fp16 operands, fp32 accumulate:
+ *
+ *   acc[m, n] = sum_k A[m, k] * B[n, k]
+ *   v         = alpha * acc + bias[n] + film[m / rows_per_sample, n] + residual[m, n]
+ *   out       = act(v)   written as fp16 and/or fp32, row stride ldo
+ *
+ * A is one or two NHWC fp16 tensors concatenated along channels (the UNet skip concat,
+ * openaimodel.py:736, folded into the K loop). taps = 1: plain [rows, C] matrix (nn.Linear, 1x1 conv:
+ * attention.py:161-168,233-248; openaimodel.py:241). taps = 9: 3x3 conv, stride 1, zero pad 1
+ * (openaimodel.py:204,230,519,685; model.py:44-50,94-118) with B laid out [n, 9*(c0+c1)], k = tap*(c0+c1)+c.
+ * c0 and c1 must be multiples of 64.
+ */
+typedef struct sdb_gemm_desc {
+  const void* a0;        /* fp16 [nb, h, w, c0] */
+  const void* a1;        /* fp16 [nb, h, w, c1] or NULL */
+  int32_t c0, c1;
+  int32_t nb, h, w;      /* rows M = nb*h*w */
+  int32_t taps;          /* 1 or 9 */
+  const void* b;         /* fp16 [n, taps*(c0+c1)] */
+  int32_t n;
+  float alpha;
+  const float* bias;     /* [n] or NULL */
+  const float* film;     /* [M / rows_per_sample, ldf] or NULL (timestep FiLM add, openaimodel.py:271-274) */
+  int32_t ldf;           /* row stride of film (0 = n) */
+  int32_t rows_per_sample;
+  const float* residual; /* fp32 [M, ldr] or NULL */
+  int32_t ldr;
+  int32_t act;           /* SDB_ACT_* */
+  void* out_f16;         /* fp16 [M, ldo] or NULL */
+  float* out_f32;        /* fp32 [M, ldo] or NULL */
+  int32_t ldo;           /* 0 = dense (n, or n/2 for GEGLU) */
+  int32_t block_n;       /* 0 = auto; else one of 32,64,128,160,256 */
+  int32_t splits;        /* split-K factor (<=1: none); needs workspace of splits*M*n floats */
+  float* workspace;
+} sdb_gemm_desc;
+
+int sdb_gemm(const sdb_gemm_desc* d, sdb_stream_t stream);
+
+/*
+ * Fused multi-head attention (flash-style, S/P/O in TMEM), replaces CrossAttention.forward's
+ * einsum -> scale -> softmax -> einsum (ldm/modules/attention.py:178-192) without materialising N x N.
+ *   q  : fp16 [batch, nq,  heads*dpad]   (row stride ldq elements; head h at column h*dpad)
+ *   k  : fp16 [batch, nkv, heads*dpad]   (row stride ldk)
+ *   vt : fp16 [batch, heads*dpad, ldvt]  (V transposed: channel-major, nkv valid columns)
+ *   out: fp16 [batch, nq, heads*d]       (row stride ldo; unpadded head dim d)
+ * dpad in {64,128,192} (head dim zero-padded to a multiple of 64 by the projection weights).
+ * scale multiplies q.k before softmax (applied after the dot product, attention.py:180).
+ * causal != 0 masks kv index > q index (CLIP text encoder).
+ */
+typedef struct sdb_attn_desc {
+  const void* q;
+  const void* k;
+  const void* vt;
+  void* out;
+  int32_t batch, heads, nq, nkv, d, dpad;
+  int32_t ldq, ldk, ldvt, ldo;
+  int64_t q_batch_stride, k_batch_stride, vt_batch_stride, o_batch_stride; /* elements */
+  float scale;
+  int32_t causal;
+} sdb_attn_desc;
+
+int sdb_attention(const sdb_attn_desc* d, sdb_stream_t stream);
+
+/*
+ * GroupNorm(32) [+ SiLU] over NHWC fp32 input that may be the channel concat of two tensors
+ * (ldm/modules/diffusionmodules/util.py:199-216 GroupNorm32 in fp32; attention.py:76-77 Normalize eps 1e-6;
+ * model.py:38-39). Statistics in fp32 (two-pass, per (sample, group)). Writes the normalised fp16 operand
+ * for the following conv and optionally a raw fp16 cast of the (concatenated) input for the 1x1 skip conv.
+ */
+int sdb_groupnorm(const float* x0, const float* x1, int32_t c0, int32_t c1, int32_t nb, int32_t hw, int32_t groups,
+                  const float* gamma, const float* beta, float eps, int32_t silu, void* out_f16, void* raw_f16,
+                  void* stats_ws /* 2*nb*groups doubles, zeroed by the call */, sdb_stream_t stream);
+
+/* LayerNorm over the last dim of fp32 [rows, c] -> fp16 (attention.py:203-205, eps 1e-5). */
+int sdb_layernorm(const float* x, int32_t rows, int32_t c, const float* gamma, const float* beta, float eps,
+                  void* out_f16, float* out_f32 /* optional */, sdb_stream_t stream);
+
+/* Row softmax of fp32 [rows, cols] * scale -> fp16 (VAE AttnBlock, model.py:191-194). */
+int sdb_softmax_rows(const float* x, int32_t rows, int32_t cols, float scale, void* out_f16, sdb_stream_t stream);
+
+/* ---- layout / elementwise helpers ---- */
+/* NCHW fp32 -> NHWC fp32 (+ optional fp16 copy); NHWC fp32 -> NCHW fp32 */
+int sdb_nchw_to_nhwc(const float* x, int32_t nb, int32_t c, int32_t hw, float* out_f32, void* out_f16,
+                     sdb_stream_t stream);
+int sdb_nhwc_to_nchw(const float* x, int32_t nb, int32_t c, int32_t hw, float* out, sdb_stream_t stream);
+/* explicit im2col for the few convs the TMA path does not cover (C_in not a multiple of 64, stride 2,
+ * asymmetric pad): out fp16 [nb*ho*wo, kpad], k = (ky*3+kx)*c + ch, zero padded to kpad.
+ * pad_lo applies top/left, bottom/right pad is implied by ho/wo (openaimodel.py:149-153; model.py:72-76). */
+int sdb_im2col3x3(const float* x, int32_t nb, int32_t h, int32_t w, int32_t c, int32_t stride, int32_t pad_lo,
+                  int32_t ho, int32_t wo, int32_t kpad, void* out_f16, sdb_stream_t stream);
+/* nearest 2x upsample NHWC fp32 -> fp16 (openaimodel.py:116; model.py:54) */
+int sdb_upsample2x(const float* x, int32_t nb, int32_t h, int32_t w, int32_t c, void* out_f16, sdb_stream_t stream);
+/* fp32 -> fp16 cast, optional transpose of [rows, cols] per batch into [cols, ldo] */
+int sdb_cast_f16(const float* x, int64_t n, void* out_f16, sdb_stream_t stream);
+int sdb_transpose_f16(const void* x, int32_t batch, int32_t rows, int32_t cols, int32_t ldx, void* out,
+                      int32_t ldo, sdb_stream_t stream);
+/* sinusoidal timestep embedding [cos | sin] (util.py:151-171): t[n] -> fp16 [n, dim] */
+int sdb_timestep_embedding(const float* t, int32_t n, int32_t dim, float max_period, void* out_f16,
+                           sdb_stream_t stream);
+/* y = silu(x) fp32 -> fp16 */
+int sdb_silu_f16(const float* x, int64_t n, void* out_f16, sdb_stream_t stream);
+
+/*
+ * One fused sampler update (classifier-free guidance + PLMS / DDIM step), replacing ~25 elementwise
+ * launches per step (ldm/models/diffusion/plms.py:182-186,199-236; ddim.py:174-204).
+ *   eps2   : fp32 [2, n] = [e_uncond; e_cond] (or [1, n] when guidance is off: scale==1)
+ *   e_t    = e_uncond + scale * (e_cond - e_uncond)
+ *   order 0: e' = e_t (DDIM / first PLMS half-step); 1..3: Adams-Bashforth with old eps h1,h2,h3
+ *   order 4 (PLMS step 0 second half): e' = (e_t_old + e_t)/2 where e_t_old = h1
+ *   pred_x0 = (x - sqrt(1-a_t) e') / sqrt(a_t);  x_prev = sqrt(a_prev) pred_x0 + sqrt(1-a_prev-sigma^2) e' + sigma*noise
+ * coef = {a_t, a_prev, sigma_t, sqrt_one_minus_a_t}; e_t is written to e_out (for the multistep history).
+ */
+int sdb_sampler_step(const float* x, const float* eps2, int32_t guided, float scale, int32_t order, const float* h1,
+                     const float* h2, const float* h3, const float* noise, float a_t, float a_prev, float sigma_t,
+                     float sqrt_one_minus_a_t, int64_t n, float* x_prev, float* pred_x0, float* e_out,
+                     sdb_stream_t stream);
+
+/* VAE posterior sample + scale (distributions.py:24-37, ddpm.py:542-549): moments NHWC fp32 [rows, 8]
+ * -> z NCHW. And image post-process clamp((x+1)/2,0,1)*255 -> uint8 NHWC (txt2img.py:314-324). */
+int sdb_vae_sample(const float* moments, const float* noise_nchw, int32_t nb, int32_t hw, float scale_factor,
+                   float* z_nchw, sdb_stream_t stream);
+int sdb_to_uint8(const float* x_nhwc, int64_t n, uint8_t* out, sdb_stream_t stream);
+/* out = a*x + b (latent scaling z/0.18215, ddpm.py:713) */
+int sdb_axpby(const float* x, float a, float b, int64_t n, float* out, sdb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDB200_H */

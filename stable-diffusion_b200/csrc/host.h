@@ -1,0 +1,37 @@
+// Host-side helpers shared by the launchers: error reporting and TMA descriptor encoding.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sdb {
+
+// Last error string for the C-ABI (sdb_last_error). Thread-local: one engine per process/device.
+void set_error(const char* fmt, ...);
+const char* last_error();
+
+#define SDB_CHECK(cond, ...)              \
+  do {                                    \
+    if (!(cond)) {                        \
+      ::sdb::set_error(__VA_ARGS__);      \
+      return 1;                           \
+    }                                     \
+  } while (0)
+
+#define SDB_CUDA(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) {                                                                    \
+      ::sdb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return 2;                                                                                 \
+    }                                                                                           \
+  } while (0)
+
+// fp16 tiled tensor map with SWIZZLE_128B and zero OOB fill. rank<=4; dims/strides innermost first;
+// strides_bytes[i] is the byte stride of dim i+1 (dim 0 is contiguous). Returns 0 on success.
+int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box);
+
+int sm_count();
+
+}  // namespace sdb

@@ -1,0 +1,227 @@
+// GroupNorm(32)[+SiLU] over (optionally concatenated) NHWC fp32 activations, LayerNorm, row softmax.
+// HBM/L2-bound streaming kernels: fp32 statistics (fp64 cross-block combine), fp16 operand output for the
+// tensor-core kernels. Reference: ldm/modules/diffusionmodules/util.py:199-216 (GroupNorm32, fp32),
+// ldm/modules/attention.py:76-77 (Normalize, eps 1e-6), :203-205 (LayerNorm), ldm/modules/diffusionmodules/model.py:38-39.
+#include "../../include/sdb200.h"
+#include "host.h"
+#include <cuda_fp16.h>
+
+namespace sdb {
+
+constexpr int GN_THREADS = 256;
+constexpr int GN_MAX_CPT = 12;  // channels per thread: C <= 3072
+
+// pass 1: per (sample, group) sum / sum of squares.  grid = (slabs, nb)
+__global__ void __launch_bounds__(GN_THREADS)
+    gn_stats_kernel(const float* __restrict__ x0, const float* __restrict__ x1, int c0, int c1, int hw, int groups,
+                    int rows_per_block, double* __restrict__ stats) {
+  const int C = c0 + c1;
+  const int cpg = C / groups;
+  const int n = blockIdx.y;
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(hw, r0 + rows_per_block);
+  __shared__ double gs[64][2];
+  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) (&gs[0][0])[i] = 0.0;
+  __syncthreads();
+  float s[GN_MAX_CPT], q[GN_MAX_CPT];
+#pragma unroll
+  for (int j = 0; j < GN_MAX_CPT; ++j) s[j] = q[j] = 0.f;
+  for (int r = r0; r < r1; ++r) {
+    const float* p0 = x0 + (static_cast<size_t>(n) * hw + r) * c0;
+    const float* p1 = x1 ? x1 + (static_cast<size_t>(n) * hw + r) * c1 : nullptr;
+#pragma unroll
+    for (int j = 0; j < GN_MAX_CPT; ++j) {
+      int c = threadIdx.x + j * GN_THREADS;
+      if (c < C) {
+        float v = c < c0 ? p0[c] : p1[c - c0];
+        s[j] += v;
+        q[j] += v * v;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < GN_MAX_CPT; ++j) {
+    int c = threadIdx.x + j * GN_THREADS;
+    if (c < C) {
+      int g = c / cpg;
+      atomicAdd(&gs[g][0], static_cast<double>(s[j]));
+      atomicAdd(&gs[g][1], static_cast<double>(q[j]));
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x)
+    atomicAdd(&stats[static_cast<size_t>(n) * groups * 2 + i], (&gs[0][0])[i]);
+}
+
+// pass 2: normalise (+SiLU) -> fp16, optional raw fp16 cast. grid = (slabs, nb)
+__global__ void __launch_bounds__(GN_THREADS)
+    gn_apply_kernel(const float* __restrict__ x0, const float* __restrict__ x1, int c0, int c1, int hw, int groups,
+                    int rows_per_block, const double* __restrict__ stats, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, float eps, int silu, __half* __restrict__ out,
+                    __half* __restrict__ raw) {
+  const int C = c0 + c1;
+  const int cpg = C / groups;
+  const int n = blockIdx.y;
+  __shared__ float mean_s[64], rstd_s[64];
+  if (threadIdx.x < groups) {
+    double cnt = static_cast<double>(hw) * cpg;
+    double m = stats[(static_cast<size_t>(n) * groups + threadIdx.x) * 2] / cnt;
+    double v = stats[(static_cast<size_t>(n) * groups + threadIdx.x) * 2 + 1] / cnt - m * m;
+    if (v < 0) v = 0;
+    mean_s[threadIdx.x] = static_cast<float>(m);
+    rstd_s[threadIdx.x] = static_cast<float>(1.0 / sqrt(v + static_cast<double>(eps)));
+  }
+  __syncthreads();
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(hw, r0 + rows_per_block);
+  const int c4 = C / 4;  // C is a multiple of 4 (checked on the host); c0 too
+  const int total = (r1 - r0) * c4;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    int r = r0 + i / c4;
+    int c = (i % c4) * 4;
+    size_t row = static_cast<size_t>(n) * hw + r;
+    float4 v = c < c0 ? *reinterpret_cast<const float4*>(x0 + row * c0 + c)
+                      : *reinterpret_cast<const float4*>(x1 + row * c1 + (c - c0));
+    float in[4] = {v.x, v.y, v.z, v.w};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int g = (c + j) / cpg;
+      float y = (in[j] - mean_s[g]) * rstd_s[g] * gamma[c + j] + beta[c + j];
+      if (silu) y = y / (1.0f + __expf(-y));
+      o[j] = y;
+    }
+    __half2 h0 = __floats2half2_rn(o[0], o[1]), h1 = __floats2half2_rn(o[2], o[3]);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&h0);
+    u.y = *reinterpret_cast<uint32_t*>(&h1);
+    *reinterpret_cast<uint2*>(out + row * C + c) = u;
+    if (raw) {
+      __half2 r0h = __floats2half2_rn(in[0], in[1]), r1h = __floats2half2_rn(in[2], in[3]);
+      uint2 w;
+      w.x = *reinterpret_cast<uint32_t*>(&r0h);
+      w.y = *reinterpret_cast<uint32_t*>(&r1h);
+      *reinterpret_cast<uint2*>(raw + row * C + c) = w;
+    }
+  }
+}
+
+// LayerNorm: one warp per row, row held in registers (C <= 32*LN_MAX_PER_LANE).
+constexpr int LN_MAX_PER_LANE = 48;
+__global__ void __launch_bounds__(256)
+    layernorm_kernel(const float* __restrict__ x, int rows, int C, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, float eps, __half* __restrict__ out, float* __restrict__ out32) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float* p = x + static_cast<size_t>(warp) * C;
+  float v[LN_MAX_PER_LANE];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < LN_MAX_PER_LANE; ++j) {
+    int c = lane + j * 32;
+    v[j] = c < C ? p[c] : 0.f;
+    s += v[j];
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  float mean = s / C;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < LN_MAX_PER_LANE; ++j) {
+    int c = lane + j * 32;
+    float d = c < C ? v[j] - mean : 0.f;
+    q += d * d;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  float rstd = rsqrtf(q / C + eps);
+#pragma unroll
+  for (int j = 0; j < LN_MAX_PER_LANE; ++j) {
+    int c = lane + j * 32;
+    if (c < C) {
+      float y = (v[j] - mean) * rstd * gamma[c] + beta[c];
+      if (out) out[static_cast<size_t>(warp) * C + c] = __float2half_rn(y);
+      if (out32) out32[static_cast<size_t>(warp) * C + c] = y;
+    }
+  }
+}
+
+// Row softmax: one block per row.
+__global__ void __launch_bounds__(256)
+    softmax_rows_kernel(const float* __restrict__ x, int cols, float scale, __half* __restrict__ out) {
+  const float* p = x + static_cast<size_t>(blockIdx.x) * cols;
+  __half* o = out + static_cast<size_t>(blockIdx.x) * cols;
+  __shared__ float red[32];
+  float m = -INFINITY;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) m = fmaxf(m, p[c] * scale);
+  for (int k = 16; k; k >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, k));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = red[0];
+  for (int w = 1; w < (blockDim.x >> 5); ++w) m = fmaxf(m, red[w]);
+  __syncthreads();
+  float s = 0.f;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) s += __expf(p[c] * scale - m);
+  for (int k = 16; k; k >>= 1) s += __shfl_xor_sync(0xffffffffu, s, k);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  s = 0.f;
+  for (int w = 0; w < (blockDim.x >> 5); ++w) s += red[w];
+  float inv = 1.0f / s;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) o[c] = __float2half_rn(__expf(p[c] * scale - m) * inv);
+}
+
+}  // namespace sdb
+
+using namespace sdb;
+
+extern "C" int sdb_groupnorm(const float* x0, const float* x1, int32_t c0, int32_t c1, int32_t nb, int32_t hw,
+                             int32_t groups, const float* gamma, const float* beta, float eps, int32_t silu,
+                             void* out_f16, void* raw_f16, void* stats_ws, sdb_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int C = c0 + c1;
+  SDB_CHECK(x0 && out_f16 && stats_ws && gamma && beta, "sdb_groupnorm: null pointer");
+  SDB_CHECK((c1 == 0) == (x1 == nullptr), "sdb_groupnorm: x1/c1 mismatch");
+  SDB_CHECK(groups > 0 && groups <= 64 && C % groups == 0, "sdb_groupnorm: C=%d not divisible by groups=%d", C, groups);
+  SDB_CHECK(c0 % 4 == 0 && c1 % 4 == 0, "sdb_groupnorm: channel counts must be multiples of 4");
+  SDB_CHECK(C <= GN_THREADS * GN_MAX_CPT, "sdb_groupnorm: C=%d too large", C);
+  size_t stats_bytes = static_cast<size_t>(nb) * groups * 2 * sizeof(double);
+  SDB_CUDA(cudaMemsetAsync(stats_ws, 0, stats_bytes, st));
+  // enough blocks to fill the machine, >= 8 rows per block
+  int target_blocks = sm_count() * 4;
+  int slabs = std::max(1, std::min((hw + 7) / 8, (target_blocks + nb - 1) / nb));
+  int rows_per_block = (hw + slabs - 1) / slabs;
+  slabs = (hw + rows_per_block - 1) / rows_per_block;
+  dim3 grid(slabs, nb);
+  gn_stats_kernel<<<grid, GN_THREADS, 0, st>>>(x0, x1, c0, c1, hw, groups, rows_per_block,
+                                               static_cast<double*>(stats_ws));
+  SDB_CUDA(cudaGetLastError());
+  gn_apply_kernel<<<grid, GN_THREADS, 0, st>>>(x0, x1, c0, c1, hw, groups, rows_per_block,
+                                               static_cast<const double*>(stats_ws), gamma, beta, eps, silu,
+                                               static_cast<__half*>(out_f16), static_cast<__half*>(raw_f16));
+  SDB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int sdb_layernorm(const float* x, int32_t rows, int32_t c, const float* gamma, const float* beta, float eps,
+                             void* out_f16, float* out_f32, sdb_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SDB_CHECK(x && gamma && beta && (out_f16 || out_f32), "sdb_layernorm: null pointer");
+  SDB_CHECK(c <= 32 * LN_MAX_PER_LANE, "sdb_layernorm: C=%d too large", c);
+  int warps_per_block = 8;
+  int blocks = (rows + warps_per_block - 1) / warps_per_block;
+  layernorm_kernel<<<blocks, warps_per_block * 32, 0, st>>>(x, rows, c, gamma, beta, eps,
+                                                            static_cast<__half*>(out_f16), out_f32);
+  SDB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int sdb_softmax_rows(const float* x, int32_t rows, int32_t cols, float scale, void* out_f16,
+                                sdb_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SDB_CHECK(x && out_f16, "sdb_softmax_rows: null pointer");
+  softmax_rows_kernel<<<rows, 256, 0, st>>>(x, cols, scale, static_cast<__half*>(out_f16));
+  SDB_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,281 @@
+"""Tensor-level wrappers over the C ABI: PyTorch tensors in/out (device memory + current stream only).
+
+Every function enqueues hand-written sm_100a kernels from libsdb200.so on the current CUDA stream; none of
+them computes with torch. Shapes follow the engine's layouts: activations NHWC, fp32 residual stream,
+fp16 tensor-core operands.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import lib as _l
+from .lib import ACT_GEGLU, ACT_NONE, ACT_QUICK_GELU, ACT_SILU, AttnDesc, GemmDesc  # noqa: F401
+
+LAUNCHES = 0  # kernels enqueued through this module (bench.py's gpu_launches claim)
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _count(n=1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _chk16(t, name):
+    assert t.dtype == torch.float16 and t.is_cuda and t.is_contiguous(), f"{name}: need contiguous cuda fp16"
+
+
+def _chk32(t, name):
+    assert t.dtype == torch.float32 and t.is_cuda and t.is_contiguous(), f"{name}: need contiguous cuda fp32"
+
+
+def gemm(a0, b, *, a1=None, nb=None, h=None, w=None, taps=1, bias=None, film=None, rows_per_sample=0,
+         residual=None, act=ACT_NONE, alpha=1.0, out_f16=None, out_f32=None, want_f16=False, want_f32=False,
+         n=None, block_n=0, splits=0, workspace=None):
+    """acc = A @ B^T with fused epilogue (see sdb_gemm in include/sdb200.h).
+
+    a0 (, a1): fp16 [..., c0] (, [..., c1]) NHWC activations or plain [rows, c] matrices.
+    b: fp16 [n, taps*(c0+c1)].
+    Returns (out_f16, out_f32) — whichever were requested / passed.
+    """
+    _chk16(a0, "a0")
+    _chk16(b, "b")
+    c0 = a0.shape[-1]
+    c1 = 0
+    if a1 is not None:
+        _chk16(a1, "a1")
+        c1 = a1.shape[-1]
+        assert a1.shape[:-1] == a0.shape[:-1]
+    if taps == 9:
+        assert a0.dim() == 4, "3x3 conv needs NHWC input"
+        nb, h, w = a0.shape[0], a0.shape[1], a0.shape[2]
+    else:
+        rows = a0.numel() // c0
+        nb, h, w = 1, 1, rows
+    n = b.shape[0] if n is None else n
+    assert b.shape[1] == taps * (c0 + c1), (b.shape, taps, c0, c1)
+    M = nb * h * w
+    n_out = n // 2 if act == ACT_GEGLU else n
+    if out_f16 is None and want_f16:
+        out_f16 = torch.empty((M, n_out), dtype=torch.float16, device=a0.device)
+    if out_f32 is None and want_f32:
+        out_f32 = torch.empty((M, n_out), dtype=torch.float32, device=a0.device)
+    assert out_f16 is not None or out_f32 is not None
+    d = GemmDesc()
+    d.a0, d.a1, d.c0, d.c1 = _ptr(a0), _ptr(a1), c0, c1
+    d.nb, d.h, d.w, d.taps = nb, h, w, taps
+    d.b, d.n, d.alpha = _ptr(b), n, alpha
+    d.bias = _ptr(bias)
+    d.film = _ptr(film)
+    d.ldf = film.stride(0) if film is not None else 0
+    d.rows_per_sample = rows_per_sample
+    d.residual = _ptr(residual)
+    d.ldr = residual.shape[-1] if residual is not None else 0
+    d.act = act
+    d.out_f16, d.out_f32 = _ptr(out_f16), _ptr(out_f32)
+    d.ldo = 0
+    d.block_n = block_n
+    d.splits = splits
+    if splits and splits > 1:
+        if workspace is None:
+            workspace = torch.empty((splits, M, n), dtype=torch.float32, device=a0.device)
+        assert workspace.numel() >= splits * M * n
+        d.workspace = _ptr(workspace)
+    _l.check(_l.load().sdb_gemm(C.byref(d), _stream()), "sdb_gemm")
+    _count(2 if splits and splits > 1 else 1)
+    return out_f16, out_f32
+
+
+def attention(q, k, vt, *, heads, d, dpad, nq, nkv, scale, causal=False, out=None):
+    """q [B, nq, heads*dpad], k [B, nkv, heads*dpad], vt [B, heads*dpad, ldvt] fp16 -> out [B, nq, heads*d] fp16."""
+    _chk16(q, "q")
+    _chk16(k, "k")
+    _chk16(vt, "vt")
+    B = q.shape[0]
+    if out is None:
+        out = torch.empty((B, nq, heads * d), dtype=torch.float16, device=q.device)
+    a = AttnDesc()
+    a.q, a.k, a.vt, a.out = _ptr(q), _ptr(k), _ptr(vt), _ptr(out)
+    a.batch, a.heads, a.nq, a.nkv, a.d, a.dpad = B, heads, nq, nkv, d, dpad
+    a.ldq, a.ldk, a.ldvt, a.ldo = q.stride(1), k.stride(1), vt.stride(1), out.stride(1)
+    a.q_batch_stride, a.k_batch_stride = q.stride(0), k.stride(0)
+    a.vt_batch_stride, a.o_batch_stride = vt.stride(0), out.stride(0)
+    a.scale, a.causal = scale, 1 if causal else 0
+    _l.check(_l.load().sdb_attention(C.byref(a), _stream()), "sdb_attention")
+    _count()
+    return out
+
+
+_gn_ws = {}
+
+
+def groupnorm(x0, gamma, beta, *, x1=None, groups=32, eps=1e-5, silu=False, want_raw=False):
+    """x0 (, x1): fp32 NHWC [nb, h, w, c]; returns (normalised fp16 NHWC [nb,h,w,c0+c1], raw fp16 or None)."""
+    _chk32(x0, "x0")
+    nb, h, w, c0 = x0.shape
+    c1 = 0
+    if x1 is not None:
+        _chk32(x1, "x1")
+        c1 = x1.shape[-1]
+    out = torch.empty((nb, h, w, c0 + c1), dtype=torch.float16, device=x0.device)
+    raw = torch.empty_like(out) if want_raw else None
+    key = (x0.device, nb, groups)
+    ws = torch.empty(2 * nb * groups, dtype=torch.float64, device=x0.device)
+    _l.check(_l.load().sdb_groupnorm(_ptr(x0), _ptr(x1), c0, c1, nb, h * w, groups, _ptr(gamma), _ptr(beta),
+                                     eps, 1 if silu else 0, _ptr(out), _ptr(raw), _ptr(ws), _stream()),
+             "sdb_groupnorm")
+    _count(3)
+    return out, raw
+
+
+def layernorm(x, gamma, beta, eps=1e-5, want_f32=False):
+    """x fp32 [rows, c] -> fp16 [rows, c]."""
+    _chk32(x, "x")
+    c = x.shape[-1]
+    rows = x.numel() // c
+    out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    out32 = torch.empty_like(x) if want_f32 else None
+    _l.check(_l.load().sdb_layernorm(_ptr(x), rows, c, _ptr(gamma), _ptr(beta), eps, _ptr(out), _ptr(out32),
+                                     _stream()), "sdb_layernorm")
+    _count()
+    return (out, out32) if want_f32 else out
+
+
+def softmax_rows(x, scale):
+    _chk32(x, "x")
+    cols = x.shape[-1]
+    rows = x.numel() // cols
+    out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    _l.check(_l.load().sdb_softmax_rows(_ptr(x), rows, cols, scale, _ptr(out), _stream()), "sdb_softmax_rows")
+    _count()
+    return out
+
+
+def nchw_to_nhwc(x, want_f32=True, want_f16=False):
+    _chk32(x, "x")
+    nb, c, h, w = x.shape
+    o32 = torch.empty((nb, h, w, c), dtype=torch.float32, device=x.device) if want_f32 else None
+    o16 = torch.empty((nb, h, w, c), dtype=torch.float16, device=x.device) if want_f16 else None
+    _l.check(_l.load().sdb_nchw_to_nhwc(_ptr(x), nb, c, h * w, _ptr(o32), _ptr(o16), _stream()), "sdb_nchw_to_nhwc")
+    _count()
+    return o32, o16
+
+
+def nhwc_to_nchw(x, out=None):
+    _chk32(x, "x")
+    nb, h, w, c = x.shape
+    if out is None:
+        out = torch.empty((nb, c, h, w), dtype=torch.float32, device=x.device)
+    _l.check(_l.load().sdb_nhwc_to_nchw(_ptr(x), nb, c, h * w, _ptr(out), _stream()), "sdb_nhwc_to_nchw")
+    _count()
+    return out
+
+
+def im2col3x3(x, stride, pad_lo, ho, wo, kpad):
+    _chk32(x, "x")
+    nb, h, w, c = x.shape
+    out = torch.empty((nb * ho * wo, kpad), dtype=torch.float16, device=x.device)
+    _l.check(_l.load().sdb_im2col3x3(_ptr(x), nb, h, w, c, stride, pad_lo, ho, wo, kpad, _ptr(out), _stream()),
+             "sdb_im2col3x3")
+    _count()
+    return out
+
+
+def upsample2x(x):
+    _chk32(x, "x")
+    nb, h, w, c = x.shape
+    out = torch.empty((nb, 2 * h, 2 * w, c), dtype=torch.float16, device=x.device)
+    _l.check(_l.load().sdb_upsample2x(_ptr(x), nb, h, w, c, _ptr(out), _stream()), "sdb_upsample2x")
+    _count()
+    return out
+
+
+def cast_f16(x):
+    _chk32(x, "x")
+    out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    _l.check(_l.load().sdb_cast_f16(_ptr(x), x.numel(), _ptr(out), _stream()), "sdb_cast_f16")
+    _count()
+    return out
+
+
+def silu_f16(x):
+    _chk32(x, "x")
+    out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    _l.check(_l.load().sdb_silu_f16(_ptr(x), x.numel(), _ptr(out), _stream()), "sdb_silu_f16")
+    _count()
+    return out
+
+
+def transpose_f16(x, ldo=None):
+    """x fp16 [B, rows, cols] -> [B, cols, ldo] (rows valid, ldo >= rows, multiple of 8 for TMA)."""
+    _chk16(x, "x")
+    B, rows, cols = x.shape
+    if ldo is None:
+        ldo = (rows + 7) // 8 * 8
+    out = torch.zeros((B, cols, ldo), dtype=torch.float16, device=x.device)
+    _l.check(_l.load().sdb_transpose_f16(_ptr(x), B, rows, cols, cols, _ptr(out), ldo, _stream()),
+             "sdb_transpose_f16")
+    _count()
+    return out
+
+
+def timestep_embedding(t, dim, max_period=10000.0):
+    _chk32(t, "t")
+    out = torch.empty((t.numel(), dim), dtype=torch.float16, device=t.device)
+    _l.check(_l.load().sdb_timestep_embedding(_ptr(t), t.numel(), dim, max_period, _ptr(out), _stream()),
+             "sdb_timestep_embedding")
+    _count()
+    return out
+
+
+def sampler_step(x, eps2, *, guided, scale, order, hist, noise, a_t, a_prev, sigma_t, sqrt_one_minus_a_t,
+                 x_prev=None, pred_x0=None, e_out=None):
+    _chk32(x, "x")
+    _chk32(eps2, "eps2")
+    n = x.numel()
+    if x_prev is None:
+        x_prev = torch.empty_like(x)
+    if pred_x0 is None:
+        pred_x0 = torch.empty_like(x)
+    if e_out is None:
+        e_out = torch.empty_like(x)
+    h = list(hist) + [None] * (3 - len(hist))
+    _l.check(_l.load().sdb_sampler_step(_ptr(x), _ptr(eps2), 1 if guided else 0, scale, order, _ptr(h[0]),
+                                        _ptr(h[1]), _ptr(h[2]), _ptr(noise), a_t, a_prev, sigma_t,
+                                        sqrt_one_minus_a_t, n, _ptr(x_prev), _ptr(pred_x0), _ptr(e_out),
+                                        _stream()), "sdb_sampler_step")
+    _count()
+    return x_prev, pred_x0, e_out
+
+
+def vae_sample(moments, noise, nb, hw, scale_factor):
+    _chk32(moments, "moments")
+    z = torch.empty((nb, 4, hw), dtype=torch.float32, device=moments.device)
+    _l.check(_l.load().sdb_vae_sample(_ptr(moments), _ptr(noise), nb, hw, scale_factor, _ptr(z), _stream()),
+             "sdb_vae_sample")
+    _count()
+    return z
+
+
+def to_uint8(x):
+    _chk32(x, "x")
+    out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    _l.check(_l.load().sdb_to_uint8(_ptr(x), x.numel(), _ptr(out), _stream()), "sdb_to_uint8")
+    _count()
+    return out
+
+
+def axpby(x, a, b=0.0):
+    _chk32(x, "x")
+    out = torch.empty_like(x)
+    _l.check(_l.load().sdb_axpby(_ptr(x), a, b, x.numel(), _ptr(out), _stream()), "sdb_axpby")
+    _count()
+    return out

@@ -1,0 +1,221 @@
+"""GPU unit parity of each hand-written kernel against a plain PyTorch fp32 restatement of the same op.
+(Whole-model parity against the oracle lives in test_unet_gpu.py etc.)"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+
+
+def rel_l2(a, b):
+    a = a.double().flatten()
+    b = b.double().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+@pytest.fixture(scope="module")
+def S(cuda_dev):
+    import sdb200
+    return sdb200
+
+
+def _rand16(shape, dev, gen, scale=1.0):
+    return (torch.randn(shape, generator=gen, device="cpu") * scale).to(dev).half()
+
+
+@pytest.mark.parametrize("M,N,K,bn", [
+    (128, 128, 64, 128), (256, 128, 128, 128), (154, 320, 768, 0), (8192, 320, 320, 160), (1000, 96, 192, 32),
+    (512, 64, 1280, 64), (384, 512, 256, 256), (128, 1280, 1280, 0), (300, 4, 320, 0),
+])
+def test_gemm_plain(S, cuda_dev, M, N, K, bn):
+    g = torch.Generator().manual_seed(M * 7 + N)
+    a = _rand16((M, K), cuda_dev, g)
+    b = _rand16((N, K), cuda_dev, g, K ** -0.5)
+    bias = torch.randn(N, generator=g).to(cuda_dev)
+    res = torch.randn(M, N, generator=g).to(cuda_dev)
+    o16, o32 = S.ops.gemm(a, b, bias=bias, residual=res, want_f16=True, want_f32=True, block_n=bn)
+    torch.cuda.synchronize()
+    ref = a.float() @ b.float().t() + bias + res
+    assert rel_l2(o32, ref) < 2e-6, rel_l2(o32, ref)
+    assert rel_l2(o16.float(), ref) < 6e-4
+
+
+@pytest.mark.parametrize("nb,h,w,c,n", [
+    (2, 16, 16, 64, 128), (2, 8, 8, 128, 64), (3, 8, 8, 64, 32), (1, 64, 64, 320, 320), (2, 32, 32, 640, 640),
+    (1, 12, 12, 64, 64), (2, 24, 24, 128, 96), (1, 128, 128, 128, 128), (2, 64, 64, 320, 4),
+])
+def test_conv3x3(S, cuda_dev, nb, h, w, c, n):
+    g = torch.Generator().manual_seed(nb * 131 + h + c)
+    x = _rand16((nb, h, w, c), cuda_dev, g)
+    wt = _rand16((n, c, 3, 3), cuda_dev, g, (9 * c) ** -0.5)
+    bias = torch.randn(n, generator=g).to(cuda_dev)
+    film = torch.randn(nb, n, generator=g).to(cuda_dev)
+    wk = wt.permute(0, 2, 3, 1).reshape(n, 9 * c).contiguous()  # [n, (ky,kx,c)]
+    _, o32 = S.ops.gemm(x, wk, taps=9, bias=bias, film=film, want_f32=True)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, padding=1) + film[:, :, None, None]
+    ref = ref.permute(0, 2, 3, 1).reshape(nb * h * w, n)
+    assert rel_l2(o32, ref) < 2e-6, rel_l2(o32, ref)
+
+
+def test_conv3x3_concat_and_skip(S, cuda_dev):
+    g = torch.Generator().manual_seed(5)
+    nb, h, w, c0, c1, n = 2, 16, 16, 128, 64, 128
+    x0 = _rand16((nb, h, w, c0), cuda_dev, g)
+    x1 = _rand16((nb, h, w, c1), cuda_dev, g)
+    wt = _rand16((n, c0 + c1, 3, 3), cuda_dev, g, (9 * (c0 + c1)) ** -0.5)
+    wk = wt.permute(0, 2, 3, 1).reshape(n, -1).contiguous()
+    _, o32 = S.ops.gemm(x0, wk, a1=x1, taps=9, want_f32=True)
+    xc = torch.cat([x0, x1], -1).float().permute(0, 3, 1, 2)
+    ref = F.conv2d(xc, wt.float(), padding=1).permute(0, 2, 3, 1).reshape(-1, n)
+    assert rel_l2(o32, ref) < 2e-6
+    # 1x1 skip over the concat
+    w1 = _rand16((n, c0 + c1), cuda_dev, g, (c0 + c1) ** -0.5)
+    _, s32 = S.ops.gemm(x0, w1, a1=x1, want_f32=True, residual=o32)
+    ref2 = torch.cat([x0, x1], -1).float().reshape(-1, c0 + c1) @ w1.float().t() + ref
+    assert rel_l2(s32, ref2) < 2e-6
+
+
+@pytest.mark.parametrize("splits", [2, 5, 9])
+def test_gemm_splitk(S, cuda_dev, splits):
+    g = torch.Generator().manual_seed(splits)
+    nb, h, w, c, n = 2, 8, 8, 320, 1280
+    x = _rand16((nb, h, w, c), cuda_dev, g)
+    wk = _rand16((n, 9 * c), cuda_dev, g, (9 * c) ** -0.5)
+    bias = torch.randn(n, generator=g).to(cuda_dev)
+    res = torch.randn(nb * h * w, n, generator=g).to(cuda_dev)
+    o16, o32 = S.ops.gemm(x, wk, taps=9, bias=bias, residual=res, want_f32=True, want_f16=True, splits=splits)
+    wt = wk.reshape(n, 3, 3, c).permute(0, 3, 1, 2).float()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt, bias, padding=1).permute(0, 2, 3, 1).reshape(-1, n) + res
+    assert rel_l2(o32, ref) < 2e-6
+    assert rel_l2(o16.float(), ref) < 6e-4
+
+
+def test_gemm_geglu_and_acts(S, cuda_dev):
+    g = torch.Generator().manual_seed(11)
+    M, K, inner = 300, 320, 1280
+    a = _rand16((M, K), cuda_dev, g)
+    wfull = _rand16((2 * inner, K), cuda_dev, g, K ** -0.5)   # rows [0,inner) = x, [inner, 2inner) = gate
+    bfull = torch.randn(2 * inner, generator=g).to(cuda_dev)
+    # pack: tile t holds rows x[t*64:(t+1)*64] then gate[t*64:(t+1)*64]
+    idx = []
+    for t in range(inner // 64):
+        idx += list(range(t * 64, t * 64 + 64)) + list(range(inner + t * 64, inner + t * 64 + 64))
+    idx = torch.tensor(idx, device=cuda_dev)
+    o16, _ = S.ops.gemm(a, wfull[idx].contiguous(), bias=bfull[idx].contiguous(), act=S.ops.ACT_GEGLU, want_f16=True)
+    y = a.float() @ wfull.float().t() + bfull
+    ref = y[:, :inner] * F.gelu(y[:, inner:])
+    assert o16.shape == (M, inner)
+    assert rel_l2(o16.float(), ref) < 8e-4, rel_l2(o16.float(), ref)
+    for act, fn in [(S.ops.ACT_SILU, F.silu), (S.ops.ACT_QUICK_GELU, lambda v: v * torch.sigmoid(1.702 * v))]:
+        _, o32 = S.ops.gemm(a, wfull[:256].contiguous(), bias=bfull[:256].contiguous(), act=act, want_f32=True)
+        ref = fn(a.float() @ wfull[:256].float().t() + bfull[:256])
+        assert rel_l2(o32, ref) < 1e-5
+
+
+def _attn_ref(q, k, v, scale, causal=False):
+    s = torch.einsum("bhid,bhjd->bhij", q, k) * scale
+    if causal:
+        n = s.shape[-1]
+        mask = torch.triu(torch.ones(s.shape[-2], n, device=s.device, dtype=torch.bool), 1)
+        s = s.masked_fill(mask, float("-inf"))
+    return torch.einsum("bhij,bhjd->bhid", s.softmax(-1), v)
+
+
+@pytest.mark.parametrize("B,H,nq,nkv,d,dpad,causal,amp", [
+    (2, 8, 256, 256, 40, 64, False, 1.0), (2, 8, 4096, 4096, 40, 64, False, 1.0), (2, 8, 1024, 1024, 80, 128, False, 1.0),
+    (2, 8, 256, 256, 160, 192, False, 1.0), (2, 8, 64, 64, 160, 192, False, 1.0), (2, 8, 4096, 77, 40, 64, False, 1.0),
+    (3, 8, 1024, 77, 80, 128, False, 1.0), (2, 12, 77, 77, 64, 64, True, 1.0), (1, 8, 1024, 1024, 40, 64, False, 6.0),
+    (1, 2, 200, 333, 64, 64, False, 3.0),
+])
+def test_attention(S, cuda_dev, B, H, nq, nkv, d, dpad, causal, amp):
+    g = torch.Generator().manual_seed(nq + nkv + d)
+    q = (torch.randn(B, H, nq, d, generator=g) * amp).half()
+    k = (torch.randn(B, H, nkv, d, generator=g) * amp).half()
+    v = torch.randn(B, H, nkv, d, generator=g).half()
+    scale = d ** -0.5
+    ref = _attn_ref(q.float(), k.float(), v.float(), scale, causal)          # [B,H,nq,d]
+    ref = ref.permute(0, 2, 1, 3).reshape(B, nq, H * d)
+
+    def pad_tokens(t):  # [B,H,n,d] -> [B,n,H*dpad]
+        tp = F.pad(t, (0, dpad - d))
+        return tp.permute(0, 2, 1, 3).reshape(B, t.shape[2], H * dpad).contiguous().to(cuda_dev)
+
+    qp, kp = pad_tokens(q), pad_tokens(k)
+    ld = (nkv + 7) // 8 * 8
+    vt = torch.zeros(B, H * dpad, ld, dtype=torch.float16)
+    vt[:, :, :nkv] = F.pad(v, (0, dpad - d)).permute(0, 1, 3, 2).reshape(B, H * dpad, nkv)
+    vt = vt.to(cuda_dev)
+    out = S.ops.attention(qp, kp, vt, heads=H, d=d, dpad=dpad, nq=nq, nkv=nkv, scale=scale, causal=causal)
+    torch.cuda.synchronize()
+    err = rel_l2(out.float().cpu(), ref)
+    assert err < 2e-3, err
+
+
+@pytest.mark.parametrize("nb,h,w,c0,c1,silu,eps", [
+    (2, 16, 16, 320, 0, True, 1e-5), (2, 8, 8, 1280, 1280, True, 1e-5), (2, 32, 32, 640, 320, False, 1e-6),
+    (1, 64, 64, 128, 0, True, 1e-6), (2, 16, 16, 1280, 640, True, 1e-5),
+])
+def test_groupnorm(S, cuda_dev, nb, h, w, c0, c1, silu, eps):
+    g = torch.Generator().manual_seed(c0 + c1)
+    x0 = (torch.randn(nb, h, w, c0, generator=g) * 2 + 0.5).to(cuda_dev)
+    x1 = (torch.randn(nb, h, w, c1, generator=g) - 1.0).to(cuda_dev) if c1 else None
+    C = c0 + c1
+    gamma = (1 + 0.1 * torch.randn(C, generator=g)).to(cuda_dev)
+    beta = (0.1 * torch.randn(C, generator=g)).to(cuda_dev)
+    out, raw = S.ops.groupnorm(x0, gamma, beta, x1=x1, eps=eps, silu=silu, want_raw=True)
+    xc = x0 if x1 is None else torch.cat([x0, x1], -1)
+    ref = F.group_norm(xc.permute(0, 3, 1, 2), 32, gamma, beta, eps)
+    if silu:
+        ref = F.silu(ref)
+    ref = ref.permute(0, 2, 3, 1)
+    assert rel_l2(out.float(), ref) < 5e-4
+    assert rel_l2(raw.float(), xc) < 5e-4
+
+
+def test_layernorm_softmax(S, cuda_dev):
+    g = torch.Generator().manual_seed(3)
+    for c in (320, 640, 1280, 768):
+        x = (torch.randn(77 * 3, c, generator=g) * 3 + 1).to(cuda_dev)
+        gamma = (1 + 0.1 * torch.randn(c, generator=g)).to(cuda_dev)
+        beta = (0.1 * torch.randn(c, generator=g)).to(cuda_dev)
+        out = S.ops.layernorm(x, gamma, beta, 1e-5)
+        assert rel_l2(out.float(), F.layer_norm(x, (c,), gamma, beta, 1e-5)) < 5e-4
+    x = torch.randn(100, 4096, generator=g).to(cuda_dev) * 4
+    p = S.ops.softmax_rows(x, 0.3)
+    assert rel_l2(p.float(), (x * 0.3).softmax(-1)) < 1e-3
+
+
+def test_elementwise(S, cuda_dev):
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(2, 5, 8, 8, generator=g).to(cuda_dev)
+    o32, o16 = S.ops.nchw_to_nhwc(x, want_f16=True)
+    assert torch.equal(o32, x.permute(0, 2, 3, 1).contiguous())
+    assert torch.equal(S.ops.nhwc_to_nchw(o32), x)
+    # im2col: stride 2 pad 1 and asymmetric (pad_lo 0)
+    xi = torch.randn(2, 9, 9, 4, generator=g).to(cuda_dev)
+    for stride, pad_lo, ho in [(1, 1, 9), (2, 1, 5), (2, 0, 4)]:
+        col = S.ops.im2col3x3(xi, stride, pad_lo, ho, ho, 64)
+        xp = xi.permute(0, 3, 1, 2)
+        if pad_lo == 0:
+            xp = F.pad(xp, (0, 1, 0, 1))
+            un = F.unfold(xp, 3, stride=stride)
+        else:
+            un = F.unfold(xp, 3, stride=stride, padding=1)
+        # unfold: [nb, c*9, L] with index c*9 + tap -> ours tap*c + ch
+        un = un.reshape(2, 4, 9, -1).permute(0, 3, 2, 1).reshape(-1, 36)
+        assert torch.allclose(col[:, :36].float(), un, atol=2e-3)
+        assert float(col[:, 36:].abs().max()) == 0.0
+    up = S.ops.upsample2x(o32)
+    assert torch.allclose(up.float(), F.interpolate(x, scale_factor=2, mode="nearest").permute(0, 2, 3, 1), atol=2e-3)
+    t = torch.tensor([981.0, 1.0, 500.5], device=cuda_dev)
+    te = S.ops.timestep_embedding(t, 320)
+    half = 160
+    freqs = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32, device=cuda_dev) / half)
+    args = t[:, None] * freqs[None]
+    ref = torch.cat([torch.cos(args), torch.sin(args)], -1)
+    assert float((te.float() - ref).abs().max()) < 2e-3
+    tr = S.ops.transpose_f16(o16.reshape(2, 64, 5))
+    assert tr.shape == (2, 5, 64) and torch.equal(tr, o16.reshape(2, 64, 5).transpose(1, 2))
