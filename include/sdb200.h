@@ -23,6 +23,7 @@ typedef void* sdb_stream_t; /* cudaStream_t */
 const char* sdb_last_error(void);
 int sdb_version(void);
 int sdb_sm_count(void);
+long long sdb_launch_count(void); /* kernels launched through this library since load */
 
 /* ---- epilogue activations ---- */
 enum {
@@ -66,8 +67,10 @@ typedef struct sdb_gemm_desc {
   float* out_f32;        /* fp32 [M, ldo] or NULL */
   int32_t ldo;           /* 0 = dense (n, or n/2 for GEGLU) */
   int32_t block_n;       /* 0 = auto; else one of 32,64,128,160,256 */
-  int32_t splits;        /* split-K factor (<=1: none); needs workspace of splits*M*n floats */
+  int32_t splits;        /* split-K factor: >1 explicit, 0/1 none, -1 auto (picked with block_n by the tile model,
+                            bounded by workspace_floats); split-K needs workspace of splits*M*n floats */
   float* workspace;
+  int64_t workspace_floats;
 } sdb_gemm_desc;
 
 int sdb_gemm(const sdb_gemm_desc* d, sdb_stream_t stream);
@@ -133,6 +136,12 @@ int sdb_transpose_f16(const void* x, int32_t batch, int32_t rows, int32_t cols, 
 /* sinusoidal timestep embedding [cos | sin] (util.py:151-171): t[n] -> fp16 [n, dim] */
 int sdb_timestep_embedding(const float* t, int32_t n, int32_t dim, float max_period, void* out_f16,
                            sdb_stream_t stream);
+/* fp32 variant of the above, and the small-M fp32-activation linear (time_embed MLP + all emb_layers,
+ * openaimodel.py:506-511,217-223): out[m, j] = act(x[m, :] . w[j, :] + bias[j]), w fp16 [n, k], act NONE|SILU */
+int sdb_timestep_embedding_f32(const float* t, int32_t n, int32_t dim, float max_period, float* out,
+                               sdb_stream_t stream);
+int sdb_linear_small(const float* x, int32_t m, int32_t k, const void* w_f16, int32_t n, const float* bias,
+                     int32_t act, float* out_f32, void* out_f16, sdb_stream_t stream);
 /* y = silu(x) fp32 -> fp16 */
 int sdb_silu_f16(const float* x, int64_t n, void* out_f16, sdb_stream_t stream);
 
@@ -148,7 +157,8 @@ int sdb_silu_f16(const float* x, int64_t n, void* out_f16, sdb_stream_t stream);
  */
 int sdb_sampler_step(const float* x, const float* eps2, int32_t guided, float scale, int32_t order, const float* h1,
                      const float* h2, const float* h3, const float* noise, float a_t, float a_prev, float sigma_t,
-                     float sqrt_one_minus_a_t, int64_t n, float* x_prev, float* pred_x0, float* e_out,
+                     float sqrt_one_minus_a_t, int64_t n, float* x_prev, float* x_prev2 /* optional second copy: the
+                     cond half of the guidance-doubled latent batch */, float* pred_x0, float* e_out,
                      sdb_stream_t stream);
 
 /* VAE posterior sample + scale (distributions.py:24-37, ddpm.py:542-549): moments NHWC fp32 [rows, 8]
@@ -158,6 +168,16 @@ int sdb_vae_sample(const float* moments, const float* noise_nchw, int32_t nb, in
 int sdb_to_uint8(const float* x_nhwc, int64_t n, uint8_t* out, sdb_stream_t stream);
 /* out = a*x + b (latent scaling z/0.18215, ddpm.py:713) */
 int sdb_axpby(const float* x, float a, float b, int64_t n, float* out, sdb_stream_t stream);
+/* out = a*x + b*y (DDIMSampler.stochastic_encode, ddim.py:206-220; q_sample, ddpm.py:274-277) */
+int sdb_axpby2(const float* x, const float* y, float a, float b, int64_t n, float* out, sdb_stream_t stream);
+
+/* 1x1 conv with <= 16 channels in fp32 (post_quant_conv 4->4 with the 1/scale_factor folded in as alpha,
+ * quant_conv 8->8; autoencoder.py:302-303,326,331): out[p, j] = sum_c (alpha x[p, c]) w[j, c] + b[j] */
+int sdb_pointwise_small(const float* x, int64_t npix, int32_t cin, int32_t cout, const float* w, const float* b,
+                        float alpha, float* out, sdb_stream_t stream);
+/* CLIP token + position embedding gather (transformers CLIPTextEmbeddings): ids int64 [rows] -> fp32 [rows, dim] */
+int sdb_embed_tokens(const int64_t* ids, int32_t rows, int32_t n_ctx, int32_t dim, int32_t vocab, const float* tok,
+                     const float* pos, float* out, sdb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -7,7 +7,12 @@ __version__ = "0.1.0"
 
 import sys as _sys
 
-from . import lib, ops  # noqa: E402,F401
+from . import arch, clip, diffusion, lib, ops, samplers, unet, util, vae  # noqa: E402,F401
+from .clip import FrozenCLIPEmbedder  # noqa: E402,F401
+from .diffusion import LatentDiffusion  # noqa: E402,F401
+from .samplers import DDIMSampler, PLMSSampler  # noqa: E402,F401
+from .unet import UNetModel  # noqa: E402,F401
+from .vae import AutoencoderKL  # noqa: E402,F401
 
 
 def _alias_submodules():

@@ -261,7 +261,7 @@ static int launch_attn(const CUtensorMap& q, const CUtensorMap& k, const CUtenso
     configured = true;
   }
   kern<<<grid, 192, SMEM, st>>>(q, k, v, p);
-  SDB_CUDA(cudaGetLastError());
+  SDB_LAUNCH_CHECK();
   return 0;
 }
 

@@ -138,32 +138,40 @@ __global__ void sampler_step_kernel(const float* __restrict__ x, const float* __
                                     float scale, int order, const float* __restrict__ h1,
                                     const float* __restrict__ h2, const float* __restrict__ h3,
                                     const float* __restrict__ noise, StepCoef k, size_t n, float* __restrict__ x_prev,
-                                    float* __restrict__ pred_x0, float* __restrict__ e_out) {
+                                    float* __restrict__ x_prev2, float* __restrict__ pred_x0,
+                                    float* __restrict__ e_out) {
   // fp32 arithmetic in the reference's operation order (plms.py:185-186,199-216,224-232)
   const float sqrt_a_t = sqrtf(k.a_t);
   const float sqrt_a_prev = sqrtf(k.a_prev);
-  const float dir_coef = sqrtf(1.0f - k.a_prev - k.sigma_t * k.sigma_t);
+  const float dir_coef = sqrtf(__fsub_rn(__fsub_rn(1.0f, k.a_prev), __fmul_rn(k.sigma_t, k.sigma_t)));
   GRID_STRIDE(i, n) {
     float e_t;
     if (guided) {
       float eu = eps2[i], ec = eps2[n + i];
-      e_t = eu + scale * (ec - eu);
+      e_t = __fadd_rn(eu, __fmul_rn(scale, __fsub_rn(ec, eu)));
     } else {
       e_t = eps2[i];
     }
     float ep;
     switch (order) {
-      case 1: ep = (3.0f * e_t - h1[i]) / 2.0f; break;
-      case 2: ep = (23.0f * e_t - 16.0f * h1[i] + 5.0f * h2[i]) / 12.0f; break;
-      case 3: ep = (55.0f * e_t - 59.0f * h1[i] + 37.0f * h2[i] - 9.0f * h3[i]) / 24.0f; break;
-      case 4: ep = (h1[i] + e_t) / 2.0f; break;
+      case 1: ep = __fdiv_rn(__fsub_rn(__fmul_rn(3.0f, e_t), h1[i]), 2.0f); break;
+      case 2:
+        ep = __fdiv_rn(__fadd_rn(__fsub_rn(__fmul_rn(23.0f, e_t), __fmul_rn(16.0f, h1[i])), __fmul_rn(5.0f, h2[i])), 12.0f);
+        break;
+      case 3:
+        ep = __fdiv_rn(__fsub_rn(__fadd_rn(__fsub_rn(__fmul_rn(55.0f, e_t), __fmul_rn(59.0f, h1[i])), __fmul_rn(37.0f, h2[i])),
+                                 __fmul_rn(9.0f, h3[i])), 24.0f);
+        break;
+      case 4: ep = __fdiv_rn(__fadd_rn(h1[i], e_t), 2.0f); break;
       default: ep = e_t; break;
     }
     float xv = x[i];
-    float p0 = (xv - k.sqrt_one_minus_a_t * ep) / sqrt_a_t;
-    float xp = sqrt_a_prev * p0 + dir_coef * ep;
-    if (noise) xp += k.sigma_t * noise[i];
+    // explicit rn ops: no FMA contraction, so the update matches the reference's separate fp32 tensor ops bit for bit
+    float p0 = __fdiv_rn(__fsub_rn(xv, __fmul_rn(k.sqrt_one_minus_a_t, ep)), sqrt_a_t);
+    float xp = __fadd_rn(__fmul_rn(sqrt_a_prev, p0), __fmul_rn(dir_coef, ep));
+    if (noise) xp = __fadd_rn(xp, __fmul_rn(k.sigma_t, noise[i]));
     if (x_prev) x_prev[i] = xp;
+    if (x_prev2) x_prev2[i] = xp;
     if (pred_x0) pred_x0[i] = p0;
     if (e_out) e_out[i] = e_t;
   }
@@ -193,8 +201,39 @@ __global__ void to_uint8_kernel(const float* __restrict__ x, size_t n, uint8_t* 
   }
 }
 
+__global__ void axpby2_kernel(const float* __restrict__ x, const float* __restrict__ y, float a, float b, size_t n,
+                              float* __restrict__ out) {
+  GRID_STRIDE(i, n) out[i] = __fadd_rn(__fmul_rn(a, x[i]), __fmul_rn(b, y[i]));
+}
+
 __global__ void axpby_kernel(const float* __restrict__ x, float a, float b, size_t n, float* __restrict__ out) {
   GRID_STRIDE(i, n) out[i] = a * x[i] + b;
+}
+
+// per-pixel small channel mix (1x1 conv with <= 8 channels, fp32): out[p, j] = alpha * sum_c x[p, c] w[j, c] + b[j]
+__global__ void pointwise_small_kernel(const float* __restrict__ x, size_t npix, int cin, int cout,
+                                       const float* __restrict__ w, const float* __restrict__ b, float alpha,
+                                       float* __restrict__ out) {
+  GRID_STRIDE(i, npix * cout) {
+    size_t p = i / cout;
+    int j = static_cast<int>(i - p * cout);
+    float acc = 0.f;
+    for (int c = 0; c < cin; ++c) acc = fmaf(x[p * cin + c] * alpha, w[j * cin + c], acc);
+    out[i] = acc + (b ? b[j] : 0.f);
+  }
+}
+
+// CLIP embeddings: out[b*n + i, :] = tok[ids[b, i], :] + pos[i, :]   (fp32)
+__global__ void embed_tokens_kernel(const long long* __restrict__ ids, int rows, int n_ctx, int dim, int vocab,
+                                    const float* __restrict__ tok, const float* __restrict__ pos,
+                                    float* __restrict__ out) {
+  GRID_STRIDE(i, static_cast<size_t>(rows) * dim) {
+    int r = static_cast<int>(i / dim), c = static_cast<int>(i % dim);
+    long long id = ids[r];
+    if (id < 0) id = 0;
+    if (id >= vocab) id = vocab - 1;
+    out[i] = tok[static_cast<size_t>(id) * dim + c] + pos[static_cast<size_t>(r % n_ctx) * dim + c];
+  }
 }
 
 }  // namespace sdb
@@ -207,14 +246,14 @@ extern "C" int sdb_nchw_to_nhwc(const float* x, int32_t nb, int32_t c, int32_t h
   SDB_CHECK(x && (out_f32 || out_f16), "sdb_nchw_to_nhwc: null pointer");
   dim3 grid((hw + 31) / 32, (c + 31) / 32, nb), block(32, 8);
   nchw_to_nhwc_kernel<<<grid, block, 0, ST>>>(x, c, hw, out_f32, static_cast<__half*>(out_f16));
-  SDB_CUDA(cudaGetLastError());
+  SDB_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int sdb_nhwc_to_nchw(const float* x, int32_t nb, int32_t c, int32_t hw, float* out, sdb_stream_t stream) {
   SDB_CHECK(x && out, "sdb_nhwc_to_nchw: null pointer");
   dim3 grid((hw + 31) / 32, (c + 31) / 32, nb), block(32, 8);
   nhwc_to_nchw_kernel<<<grid, block, 0, ST>>>(x, c, hw, out);
-  SDB_CUDA(cudaGetLastError());
+  SDB_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int sdb_im2col3x3(const float* x, int32_t nb, int32_t h, int32_t w, int32_t c, int32_t stride,
@@ -224,7 +263,7 @@ extern "C" int sdb_im2col3x3(const float* x, int32_t nb, int32_t h, int32_t w, i
   size_t total = static_cast<size_t>(nb) * ho * wo * kpad;
   im2col3x3_kernel<<<grid_for(total), 256, 0, ST>>>(x, nb, h, w, c, stride, pad_lo, ho, wo, kpad,
                                                     static_cast<__half*>(out_f16));
-  SDB_CUDA(cudaGetLastError());
+  SDB_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int sdb_upsample2x(const float* x, int32_t nb, int32_t h, int32_t w, int32_t c, void* out_f16,
@@ -232,19 +271,19 @@ extern "C" int sdb_upsample2x(const float* x, int32_t nb, int32_t h, int32_t w, 
   SDB_CHECK(x && out_f16 && c % 4 == 0, "sdb_upsample2x: bad arguments");
   size_t total = static_cast<size_t>(nb) * 4 * h * w * (c / 4);
   upsample2x_kernel<<<grid_for(total), 256, 0, ST>>>(x, nb, h, w, c, static_cast<__half*>(out_f16));
-  SDB_CUDA(cudaGetLastError());
+  SDB_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int sdb_cast_f16(const float* x, int64_t n, void* out_f16, sdb_stream_t stream) {
   SDB_CHECK(x && out_f16 && n >= 0, "sdb_cast_f16: bad arguments");
   cast_f16_kernel<<<grid_for(n), 256, 0, ST>>>(x, static_cast<size_t>(n), static_cast<__half*>(out_f16));
-  SDB_CUDA(cudaGetLastError());
+  SDB_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int sdb_silu_f16(const float* x, int64_t n, void* out_f16, sdb_stream_t stream) {
   SDB_CHECK(x && out_f16 && n >= 0, "sdb_silu_f16: bad arguments");
   silu_f16_kernel<<<grid_for(n), 256, 0, ST>>>(x, static_cast<size_t>(n), static_cast<__half*>(out_f16));
-  SDB_CUDA(cudaGetLastError());
+  SDB_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int sdb_transpose_f16(const void* x, int32_t batch, int32_t rows, int32_t cols, int32_t ldx, void* out,
@@ -253,7 +292,7 @@ extern "C" int sdb_transpose_f16(const void* x, int32_t batch, int32_t rows, int
   dim3 grid((rows + 31) / 32, (cols + 31) / 32, batch), block(32, 8);
   transpose_f16_kernel<<<grid, block, 0, ST>>>(static_cast<const __half*>(x), rows, cols, ldx,
                                                static_cast<__half*>(out), ldo);
-  SDB_CUDA(cudaGetLastError());
+  SDB_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int sdb_timestep_embedding(const float* t, int32_t n, int32_t dim, float max_period, void* out_f16,
@@ -261,20 +300,20 @@ extern "C" int sdb_timestep_embedding(const float* t, int32_t n, int32_t dim, fl
   SDB_CHECK(t && out_f16 && dim % 2 == 0, "sdb_timestep_embedding: bad arguments");
   timestep_embedding_kernel<<<grid_for(static_cast<size_t>(n) * dim / 2), 256, 0, ST>>>(
       t, n, dim, max_period, static_cast<__half*>(out_f16));
-  SDB_CUDA(cudaGetLastError());
+  SDB_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int sdb_sampler_step(const float* x, const float* eps2, int32_t guided, float scale, int32_t order,
                                 const float* h1, const float* h2, const float* h3, const float* noise, float a_t,
                                 float a_prev, float sigma_t, float sqrt_one_minus_a_t, int64_t n, float* x_prev,
-                                float* pred_x0, float* e_out, sdb_stream_t stream) {
+                                float* x_prev2, float* pred_x0, float* e_out, sdb_stream_t stream) {
   SDB_CHECK(x && eps2 && n > 0, "sdb_sampler_step: bad arguments");
   SDB_CHECK(order >= 0 && order <= 4, "sdb_sampler_step: order %d", order);
   SDB_CHECK((order == 0) || h1, "sdb_sampler_step: missing history");
   StepCoef k{a_t, a_prev, sigma_t, sqrt_one_minus_a_t};
   sampler_step_kernel<<<grid_for(n), 256, 0, ST>>>(x, eps2, guided, scale, order, h1, h2, h3, noise, k,
-                                                   static_cast<size_t>(n), x_prev, pred_x0, e_out);
-  SDB_CUDA(cudaGetLastError());
+                                                   static_cast<size_t>(n), x_prev, x_prev2, pred_x0, e_out);
+  SDB_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int sdb_vae_sample(const float* moments, const float* noise_nchw, int32_t nb, int32_t hw,
@@ -282,21 +321,45 @@ extern "C" int sdb_vae_sample(const float* moments, const float* noise_nchw, int
   SDB_CHECK(moments && z_nchw, "sdb_vae_sample: null pointer");
   vae_sample_kernel<<<grid_for(static_cast<size_t>(nb) * 4 * hw), 256, 0, ST>>>(moments, noise_nchw, nb, hw,
                                                                                 scale_factor, z_nchw);
-  SDB_CUDA(cudaGetLastError());
+  SDB_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int sdb_to_uint8(const float* x, int64_t n, uint8_t* out, sdb_stream_t stream) {
   SDB_CHECK(x && out, "sdb_to_uint8: null pointer");
   to_uint8_kernel<<<grid_for(n), 256, 0, ST>>>(x, static_cast<size_t>(n), out);
-  SDB_CUDA(cudaGetLastError());
+  SDB_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int sdb_axpby2(const float* x, const float* y, float a, float b, int64_t n, float* out,
+                          sdb_stream_t stream) {
+  SDB_CHECK(x && y && out, "sdb_axpby2: null pointer");
+  axpby2_kernel<<<grid_for(n), 256, 0, ST>>>(x, y, a, b, static_cast<size_t>(n), out);
+  SDB_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int sdb_axpby(const float* x, float a, float b, int64_t n, float* out, sdb_stream_t stream) {
   SDB_CHECK(x && out, "sdb_axpby: null pointer");
   axpby_kernel<<<grid_for(n), 256, 0, ST>>>(x, a, b, static_cast<size_t>(n), out);
-  SDB_CUDA(cudaGetLastError());
+  SDB_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int sdb_pointwise_small(const float* x, int64_t npix, int32_t cin, int32_t cout, const float* w,
+                                   const float* b, float alpha, float* out, sdb_stream_t stream) {
+  SDB_CHECK(x && w && out && cin > 0 && cin <= 16 && cout > 0 && cout <= 16, "sdb_pointwise_small: bad arguments");
+  pointwise_small_kernel<<<grid_for(static_cast<size_t>(npix) * cout), 256, 0, ST>>>(
+      x, static_cast<size_t>(npix), cin, cout, w, b, alpha, out);
+  SDB_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int sdb_embed_tokens(const int64_t* ids, int32_t rows, int32_t n_ctx, int32_t dim, int32_t vocab,
+                                const float* tok, const float* pos, float* out, sdb_stream_t stream) {
+  SDB_CHECK(ids && tok && pos && out, "sdb_embed_tokens: null pointer");
+  embed_tokens_kernel<<<grid_for(static_cast<size_t>(rows) * dim), 256, 0, ST>>>(
+      reinterpret_cast<const long long*>(ids), rows, n_ctx, dim, vocab, tok, pos, out);
+  SDB_LAUNCH_CHECK();
   return 0;
 }
 extern "C" const char* sdb_last_error(void) { return sdb::last_error(); }
 extern "C" int sdb_version(void) { return 100; }
 extern "C" int sdb_sm_count(void) { return sdb::sm_count(); }
+extern "C" long long sdb_launch_count(void) { return sdb::launch_count(); }

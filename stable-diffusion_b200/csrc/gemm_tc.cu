@@ -330,7 +330,7 @@ static int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
     configured = true;
   }
   kern<<<grid, 192, Cfg::SMEM, st>>>(a0, a1, b, p);
-  SDB_CUDA(cudaGetLastError());
+  SDB_LAUNCH_CHECK();
   return 0;
 }
 
@@ -340,24 +340,47 @@ static int pow2_divisor(int v, int cap) {
   return p;
 }
 
-static int pick_block_n(int n, long m_tiles, int splits, bool geglu) {
+// Tile model used to pick (block_n, split-K): every 64-wide K step of a 128 x bn tile moves (128 + bn) * 128 B
+// from L2 (the binding resource for 1-CTA tiles), the epilogue drains bn columns, plus a fixed launch/prologue cost;
+// CTAs run in waves of sm_count. Split-K adds an fp32 partial round trip and a second kernel.
+static double tile_cost(int n, long m_tiles, int k_iters, int bn, int splits, long M) {
+  long nt = (n + bn - 1) / bn;
+  long tiles = m_tiles * nt * splits;
+  long waves = (tiles + sm_count() - 1) / sm_count();
+  double per_tile = static_cast<double>((k_iters + splits - 1) / splits) * (128.0 + bn) + 2.0 * bn + 300.0;
+  double t = waves * per_tile;
+  if (splits > 1) t += 1500.0 + static_cast<double>(splits) * M * n / (sm_count() * 64.0);
+  return t;
+}
+
+static void pick_tiles(int n, long m_tiles, int k_iters, long M, bool geglu, int fixed_bn, int fixed_splits,
+                       long ws_floats, int* bn_out, int* splits_out) {
   const int cands[] = {256, 160, 128, 64, 32};
-  int best = 128;
-  double best_t = 1e30;
-  int sms = sm_count();
+  double best_t = 1e300;
+  int best_bn = 128, best_s = 1;
   for (int bn : cands) {
+    if (fixed_bn > 0 && bn != fixed_bn) continue;
     if (geglu && bn != 128) continue;
-    long nt = (n + bn - 1) / bn;
-    if (bn > 32 && nt * bn - n >= bn / 2 && n > 32) continue;  // too much padded work
-    long tiles = m_tiles * nt * (splits > 1 ? splits : 1);
-    long waves = (tiles + sms - 1) / sms;
-    double t = static_cast<double>(waves) * (bn + (bn > 128 ? 48.0 : 24.0));
-    if (t < best_t) {
-      best_t = t;
-      best = bn;
+    if (fixed_bn <= 0 && bn > 32 && ((n + bn - 1) / bn) * bn - n >= bn / 2 && n > 32) continue;  // mostly padding
+    int smax = 1;
+    if (fixed_splits == -1 && !geglu) {
+      smax = k_iters / 4;
+      if (smax > 32) smax = 32;
+      if (smax < 1) smax = 1;
+    }
+    for (int s = 1; s <= smax; ++s) {
+      if (s > 1 && static_cast<long>(s) * M * n > ws_floats) break;
+      int sp = fixed_splits > 1 ? fixed_splits : s;
+      double t = tile_cost(n, m_tiles, k_iters, bn, sp, M);
+      if (t < best_t) {
+        best_t = t;
+        best_bn = bn;
+        best_s = sp;
+      }
     }
   }
-  return best;
+  *bn_out = best_bn;
+  *splits_out = best_s;
 }
 
 }  // namespace sdb
@@ -421,17 +444,23 @@ extern "C" int sdb_gemm(const sdb_gemm_desc* d, sdb_stream_t stream) {
     m_tiles = static_cast<long>(p.tiles_x) * p.tiles_y * ((d->nb + p.TN - 1) / p.TN);
   }
 
-  int splits = d->splits > 1 ? d->splits : 1;
-  if (splits > p.k_iters) splits = p.k_iters;
-  if (splits > 1) {
-    SDB_CHECK(d->workspace != nullptr, "sdb_gemm: split-K needs a workspace");
-    p.ws = d->workspace;
+  int bn = 128, splits = 1;
+  {
+    int fixed_splits = d->splits;
+    if (fixed_splits == -1 && d->workspace == nullptr) fixed_splits = 0;
+    if (fixed_splits > p.k_iters) fixed_splits = p.k_iters;
+    pick_tiles(d->n, m_tiles, p.k_iters, M, geglu, d->block_n, fixed_splits, d->workspace_floats, &bn, &splits);
   }
+  SDB_CHECK(bn == 32 || bn == 64 || bn == 128 || bn == 160 || bn == 256, "sdb_gemm: unsupported block_n %d", bn);
+  SDB_CHECK(!geglu || bn == 128, "sdb_gemm: GEGLU requires block_n 128");
   p.iters_per_split = (p.k_iters + splits - 1) / splits;
   splits = (p.k_iters + p.iters_per_split - 1) / p.iters_per_split;
-
-  int bn = d->block_n > 0 ? d->block_n : pick_block_n(d->n, m_tiles, splits, geglu);
-  SDB_CHECK(!geglu || bn == 128, "sdb_gemm: GEGLU requires block_n 128");
+  if (splits > 1) {
+    SDB_CHECK(d->workspace != nullptr, "sdb_gemm: split-K needs a workspace");
+    SDB_CHECK(d->workspace_floats <= 0 || static_cast<long>(splits) * M * d->n <= d->workspace_floats,
+              "sdb_gemm: split-K workspace too small");
+    p.ws = d->workspace;
+  }
 
   // tensor maps
   CUtensorMap tA0, tA1, tB;
@@ -480,7 +509,7 @@ extern "C" int sdb_gemm(const sdb_gemm_desc* d, sdb_stream_t stream) {
     size_t total = static_cast<size_t>(p.M) * p.N;
     int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(sm_count()) * 8));
     splitk_epilogue_kernel<<<blocks, 256, 0, st>>>(p, splits);
-    SDB_CUDA(cudaGetLastError());
+    SDB_LAUNCH_CHECK();
   }
   return 0;
 }

@@ -60,6 +60,10 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
   return 0;
 }
 
+static long long g_launches = 0;
+void count_launch() { ++g_launches; }
+long long launch_count() { return g_launches; }
+
 int sm_count() {
   static int n = 0;
   if (!n) {

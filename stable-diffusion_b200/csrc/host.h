@@ -34,4 +34,14 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
 
 int sm_count();
 
+// kernels launched through the C ABI since load (bench.py's gpu_launches)
+void count_launch();
+long long launch_count();
+
+#define SDB_LAUNCH_CHECK()              \
+  do {                                  \
+    ::sdb::count_launch();              \
+    SDB_CUDA(cudaGetLastError());       \
+  } while (0)
+
 }  // namespace sdb

@@ -196,11 +196,11 @@ extern "C" int sdb_groupnorm(const float* x0, const float* x1, int32_t c0, int32
   dim3 grid(slabs, nb);
   gn_stats_kernel<<<grid, GN_THREADS, 0, st>>>(x0, x1, c0, c1, hw, groups, rows_per_block,
                                                static_cast<double*>(stats_ws));
-  SDB_CUDA(cudaGetLastError());
+  SDB_LAUNCH_CHECK();
   gn_apply_kernel<<<grid, GN_THREADS, 0, st>>>(x0, x1, c0, c1, hw, groups, rows_per_block,
                                                static_cast<const double*>(stats_ws), gamma, beta, eps, silu,
                                                static_cast<__half*>(out_f16), static_cast<__half*>(raw_f16));
-  SDB_CUDA(cudaGetLastError());
+  SDB_LAUNCH_CHECK();
   return 0;
 }
 
@@ -213,7 +213,7 @@ extern "C" int sdb_layernorm(const float* x, int32_t rows, int32_t c, const floa
   int blocks = (rows + warps_per_block - 1) / warps_per_block;
   layernorm_kernel<<<blocks, warps_per_block * 32, 0, st>>>(x, rows, c, gamma, beta, eps,
                                                             static_cast<__half*>(out_f16), out_f32);
-  SDB_CUDA(cudaGetLastError());
+  SDB_LAUNCH_CHECK();
   return 0;
 }
 
@@ -222,6 +222,6 @@ extern "C" int sdb_softmax_rows(const float* x, int32_t rows, int32_t cols, floa
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SDB_CHECK(x && out_f16, "sdb_softmax_rows: null pointer");
   softmax_rows_kernel<<<rows, 256, 0, st>>>(x, cols, scale, static_cast<__half*>(out_f16));
-  SDB_CUDA(cudaGetLastError());
+  SDB_LAUNCH_CHECK();
   return 0;
 }

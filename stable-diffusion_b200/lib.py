@@ -35,6 +35,7 @@ class GemmDesc(C.Structure):
         ("block_n", C.c_int32),
         ("splits", C.c_int32),
         ("workspace", C.c_void_p),
+        ("workspace_floats", C.c_int64),
     ]
 
 
@@ -57,6 +58,7 @@ SIGNATURES = {
     "sdb_last_error": ([], C.c_char_p),
     "sdb_version": ([], C.c_int),
     "sdb_sm_count": ([], C.c_int),
+    "sdb_launch_count": ([], C.c_longlong),
     "sdb_gemm": ([C.POINTER(GemmDesc), _P], C.c_int),
     "sdb_attention": ([C.POINTER(AttnDesc), _P], C.c_int),
     "sdb_groupnorm": ([_P, _P, _I, _I, _I, _I, _I, _P, _P, _F, _I, _P, _P, _P, _P], C.c_int),
@@ -69,11 +71,16 @@ SIGNATURES = {
     "sdb_cast_f16": ([_P, _L, _P, _P], C.c_int),
     "sdb_transpose_f16": ([_P, _I, _I, _I, _I, _P, _I, _P], C.c_int),
     "sdb_timestep_embedding": ([_P, _I, _I, _F, _P, _P], C.c_int),
+    "sdb_timestep_embedding_f32": ([_P, _I, _I, _F, _P, _P], C.c_int),
+    "sdb_linear_small": ([_P, _I, _I, _P, _I, _P, _I, _P, _P, _P], C.c_int),
     "sdb_silu_f16": ([_P, _L, _P, _P], C.c_int),
-    "sdb_sampler_step": ([_P, _P, _I, _F, _I, _P, _P, _P, _P, _F, _F, _F, _F, _L, _P, _P, _P, _P], C.c_int),
+    "sdb_sampler_step": ([_P, _P, _I, _F, _I, _P, _P, _P, _P, _F, _F, _F, _F, _L, _P, _P, _P, _P, _P], C.c_int),
     "sdb_vae_sample": ([_P, _P, _I, _I, _F, _P, _P], C.c_int),
     "sdb_to_uint8": ([_P, _L, _P, _P], C.c_int),
     "sdb_axpby": ([_P, _F, _F, _L, _P, _P], C.c_int),
+    "sdb_pointwise_small": ([_P, _L, _I, _I, _P, _P, _F, _P, _P], C.c_int),
+    "sdb_embed_tokens": ([_P, _I, _I, _I, _I, _P, _P, _P, _P], C.c_int),
+    "sdb_axpby2": ([_P, _P, _F, _F, _L, _P, _P], C.c_int),
 }
 
 _lib = None

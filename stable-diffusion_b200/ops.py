@@ -84,21 +84,33 @@ def gemm(a0, b, *, a1=None, nb=None, h=None, w=None, taps=1, bias=None, film=Non
     d.ldo = 0
     d.block_n = block_n
     d.splits = splits
-    if splits and splits > 1:
+    if splits and (splits > 1 or splits == -1):
         if workspace is None:
-            workspace = torch.empty((splits, M, n), dtype=torch.float32, device=a0.device)
-        assert workspace.numel() >= splits * M * n
+            workspace = splitk_workspace(a0.device)
+        assert splits == -1 or workspace.numel() >= splits * M * n
         d.workspace = _ptr(workspace)
+        d.workspace_floats = workspace.numel()
     _l.check(_l.load().sdb_gemm(C.byref(d), _stream()), "sdb_gemm")
     _count(2 if splits and splits > 1 else 1)
     return out_f16, out_f32
 
 
+_WS = {}
+WS_FLOATS = 16 * 1024 * 1024
+
+
+def splitk_workspace(device):
+    """Persistent fp32 scratch for split-K partials (stream-ordered reuse: one GEMM at a time per stream)."""
+    key = (device.type, device.index)
+    if key not in _WS:
+        _WS[key] = torch.empty(WS_FLOATS, dtype=torch.float32, device=device)
+    return _WS[key]
+
+
 def attention(q, k, vt, *, heads, d, dpad, nq, nkv, scale, causal=False, out=None):
     """q [B, nq, heads*dpad], k [B, nkv, heads*dpad], vt [B, heads*dpad, ldvt] fp16 -> out [B, nq, heads*d] fp16."""
-    _chk16(q, "q")
-    _chk16(k, "k")
-    _chk16(vt, "vt")
+    for name, t_ in (("q", q), ("k", k), ("vt", vt)):
+        assert t_.dtype == torch.float16 and t_.is_cuda and t_.dim() == 3 and t_.stride(2) == 1, f"{name}: bad layout"
     B = q.shape[0]
     if out is None:
         out = torch.empty((B, nq, heads * d), dtype=torch.float16, device=q.device)
@@ -220,7 +232,7 @@ def transpose_f16(x, ldo=None):
     B, rows, cols = x.shape
     if ldo is None:
         ldo = (rows + 7) // 8 * 8
-    out = torch.zeros((B, cols, ldo), dtype=torch.float16, device=x.device)
+    out = torch.empty((B, cols, ldo), dtype=torch.float16, device=x.device)  # pad columns are never read
     _l.check(_l.load().sdb_transpose_f16(_ptr(x), B, rows, cols, cols, _ptr(out), ldo, _stream()),
              "sdb_transpose_f16")
     _count()
@@ -236,24 +248,61 @@ def timestep_embedding(t, dim, max_period=10000.0):
     return out
 
 
+def timestep_embedding_f32(t, dim, max_period=10000.0):
+    _chk32(t, "t")
+    out = torch.empty((t.numel(), dim), dtype=torch.float32, device=t.device)
+    _l.check(_l.load().sdb_timestep_embedding_f32(_ptr(t), t.numel(), dim, max_period, _ptr(out), _stream()),
+             "sdb_timestep_embedding_f32")
+    _count()
+    return out
+
+
+def linear_small(x, w, bias=None, act=ACT_NONE, want_f16=False):
+    """x fp32 [m, k] (m small), w fp16 [n, k] -> fp32 [m, n] (fp32 activations end to end)."""
+    _chk32(x, "x")
+    _chk16(w, "w")
+    m, k = x.shape
+    n = w.shape[0]
+    out = torch.empty((m, n), dtype=torch.float32, device=x.device)
+    out16 = torch.empty((m, n), dtype=torch.float16, device=x.device) if want_f16 else None
+    _l.check(_l.load().sdb_linear_small(_ptr(x), m, k, _ptr(w), n, _ptr(bias), act, _ptr(out), _ptr(out16),
+                                        _stream()), "sdb_linear_small")
+    _count()
+    return (out, out16) if want_f16 else out
+
+
 def sampler_step(x, eps2, *, guided, scale, order, hist, noise, a_t, a_prev, sigma_t, sqrt_one_minus_a_t,
-                 x_prev=None, pred_x0=None, e_out=None):
+                 x_prev=None, pred_x0=None, e_out=None, dup=False):
+    """One fused CFG + PLMS/DDIM update. x: [b,...] fp32; eps2: [2b,...] if guided else [b,...].
+    dup: x_prev is a [2b,...] buffer and both halves receive the new latent (the next step's doubled batch)."""
     _chk32(x, "x")
     _chk32(eps2, "eps2")
     n = x.numel()
     if x_prev is None:
-        x_prev = torch.empty_like(x)
+        x_prev = torch.empty((2,) + tuple(x.shape), dtype=torch.float32, device=x.device).flatten(0, 1) if dup \
+            else torch.empty_like(x)
     if pred_x0 is None:
         pred_x0 = torch.empty_like(x)
-    if e_out is None:
-        e_out = torch.empty_like(x)
+    xp2 = None
+    if dup:
+        assert x_prev.numel() == 2 * n and x_prev.is_contiguous()
+        xp2 = C.c_void_p(x_prev.data_ptr() + 4 * n)
     h = list(hist) + [None] * (3 - len(hist))
     _l.check(_l.load().sdb_sampler_step(_ptr(x), _ptr(eps2), 1 if guided else 0, scale, order, _ptr(h[0]),
                                         _ptr(h[1]), _ptr(h[2]), _ptr(noise), a_t, a_prev, sigma_t,
-                                        sqrt_one_minus_a_t, n, _ptr(x_prev), _ptr(pred_x0), _ptr(e_out),
+                                        sqrt_one_minus_a_t, n, _ptr(x_prev), xp2, _ptr(pred_x0), _ptr(e_out),
                                         _stream()), "sdb_sampler_step")
     _count()
     return x_prev, pred_x0, e_out
+
+
+def axpby2(x, y, a, b):
+    _chk32(x, "x")
+    _chk32(y, "y")
+    out = torch.empty_like(x)
+    _l.check(_l.load().sdb_axpby2(_ptr(x), _ptr(y), a, b, x.numel(), _ptr(out), _stream()), "sdb_axpby2")
+    _count()
+    return out
 
 
 def vae_sample(moments, noise, nb, hw, scale_factor):
@@ -277,5 +326,30 @@ def axpby(x, a, b=0.0):
     _chk32(x, "x")
     out = torch.empty_like(x)
     _l.check(_l.load().sdb_axpby(_ptr(x), a, b, x.numel(), _ptr(out), _stream()), "sdb_axpby")
+    _count()
+    return out
+
+
+def pointwise_small(x, w, b=None, alpha=1.0):
+    """x fp32 [..., cin] NHWC, w fp32 [cout, cin] -> fp32 [..., cout]."""
+    _chk32(x, "x")
+    _chk32(w, "w")
+    cout, cin = w.shape
+    assert x.shape[-1] == cin
+    out = torch.empty(tuple(x.shape[:-1]) + (cout,), dtype=torch.float32, device=x.device)
+    _l.check(_l.load().sdb_pointwise_small(_ptr(x), x.numel() // cin, cin, cout, _ptr(w), _ptr(b), alpha, _ptr(out),
+                                           _stream()), "sdb_pointwise_small")
+    _count()
+    return out
+
+
+def embed_tokens(ids, tok, pos):
+    """ids int64 [B, n] -> fp32 [B*n, dim]."""
+    assert ids.dtype == torch.int64 and ids.is_cuda and ids.is_contiguous()
+    B, n = ids.shape
+    dim = tok.shape[1]
+    out = torch.empty((B * n, dim), dtype=torch.float32, device=ids.device)
+    _l.check(_l.load().sdb_embed_tokens(_ptr(ids), B * n, n, dim, tok.shape[0], _ptr(tok), _ptr(pos), _ptr(out),
+                                        _stream()), "sdb_embed_tokens")
     _count()
     return out

@@ -1,0 +1,337 @@
+"""B200-native UNet for the SD-v1 denoising loop: drop-in for the reference's
+`ldm.modules.diffusionmodules.openaimodel.UNetModel` (constructor kwargs openaimodel.py:443-469,
+`forward(x, timesteps, context)` openaimodel.py:710-742, state-dict keys unchanged).
+
+Nothing here computes with torch: forward() only sequences the hand-written sm_100a kernels of libsdb200.so
+(ops.py). torch provides device memory and the current stream. nn.Module is used solely so that the reference's
+`load_state_dict` / `instantiate_from_config` plumbing (ldm/util.py:78-93, scripts/txt2img.py:49-66) sees this
+object; there are no nn layers and no parameters.
+
+Data layout: activations NHWC; the residual stream is fp32, tensor-core operands are fp16 (fp32 accumulate);
+GroupNorm/LayerNorm statistics, softmax, FiLM and residual adds are fp32.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .arch import unet_param_shapes, unet_plan
+from .ops import ACT_GEGLU, ACT_SILU
+
+
+def _dpad(d):
+    return (d + 63) // 64 * 64
+
+
+def _pack_conv3(w):  # [Cout, Cin, 3, 3] -> [Cout, 9*Cin], k = (ky*3+kx)*Cin + c
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous().half()
+
+
+def _pack_conv3_padk(w, kpad):  # small-Cin convs through im2col: K zero-padded to kpad
+    p = torch.zeros((w.shape[0], kpad), dtype=torch.float16, device=w.device)
+    p[:, : 9 * w.shape[1]] = _pack_conv3(w)
+    return p
+
+
+def _pack_heads(w, heads, d, dpad):  # [heads*d, K] -> [heads*dpad, K], zero rows between heads
+    K = w.shape[1]
+    p = torch.zeros((heads, dpad, K), dtype=torch.float16, device=w.device)
+    p[:, :d] = w.reshape(heads, d, K).half()
+    return p.reshape(heads * dpad, K).contiguous()
+
+
+def _pack_geglu(w, b):  # [8C, C]: rows [0,4C) value, [4C,8C) gate -> per 128-row tile [64 value | 64 gate]
+    inner = w.shape[0] // 2
+    assert inner % 64 == 0
+    idx = torch.arange(inner, device=w.device).reshape(-1, 64)
+    perm = torch.cat([idx, idx + inner], dim=1).reshape(-1)
+    return w[perm].contiguous().half(), b[perm].contiguous().float()
+
+
+class UNetModel(nn.Module):
+    def __init__(self, image_size, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions,
+                 dropout=0, channel_mult=(1, 2, 4, 8), conv_resample=True, dims=2, num_classes=None,
+                 use_checkpoint=False, use_fp16=False, num_heads=-1, num_head_channels=-1, num_heads_upsample=-1,
+                 use_scale_shift_norm=False, resblock_updown=False, use_new_attention_order=False,
+                 use_spatial_transformer=False, transformer_depth=1, context_dim=None, n_embed=None, legacy=True):
+        super().__init__()
+        # same argument checks as the reference (openaimodel.py:471-489)
+        if use_spatial_transformer:
+            assert context_dim is not None, "Fool!! You forgot to include the dimension of your cross-attention conditioning..."
+        if context_dim is not None:
+            assert use_spatial_transformer, "Fool!! You forgot to use the spatial transformer for your cross-attention conditioning..."
+            context_dim = list(context_dim) if isinstance(context_dim, (list, tuple)) else context_dim
+        if num_heads == -1:
+            assert num_head_channels != -1, "Either num_heads or num_head_channels has to be set"
+        # the B200 path covers the configuration SD v1 ships (v1-inference.yaml:29-44)
+        unsupported = dict(dims=dims != 2, num_classes=num_classes is not None, resblock_updown=resblock_updown,
+                           use_scale_shift_norm=use_scale_shift_norm, n_embed=n_embed is not None,
+                           no_spatial_transformer=not use_spatial_transformer, transformer_depth=transformer_depth != 1,
+                           num_head_channels=num_head_channels != -1, dropout=dropout != 0,
+                           conv_resample=not conv_resample)
+        bad = [k for k, v in unsupported.items() if v]
+        if bad:
+            raise NotImplementedError(f"sdb200.UNetModel supports the SD-v1 UNet configuration only; unsupported: {bad}")
+        self.cfg = dict(image_size=image_size, in_channels=in_channels, model_channels=model_channels,
+                        out_channels=out_channels, num_res_blocks=num_res_blocks,
+                        attention_resolutions=list(attention_resolutions), channel_mult=list(channel_mult),
+                        num_heads=num_heads, use_spatial_transformer=True, transformer_depth=1,
+                        context_dim=context_dim, legacy=legacy)
+        self.in_channels, self.model_channels, self.out_channels = in_channels, model_channels, out_channels
+        self.num_heads = num_heads
+        self.context_dim = context_dim
+        self.dtype = torch.float32
+        self.plan = unet_plan(self.cfg)
+        self.shapes = unet_param_shapes(self.cfg)
+        self.W = None           # packed weights (device)
+        self._ctx_key = None
+        self._ctx_kv = None
+        self._graphs = {}
+
+    # ------------------------------------------------------------------ weights
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                              error_msgs):
+        sub = {k[len(prefix):]: v for k, v in state_dict.items() if k.startswith(prefix)}
+        missing = [k for k in self.shapes if k not in sub]
+        if missing:
+            missing_keys.extend(prefix + k for k in missing)
+            return
+        for k in sub:
+            if k not in self.shapes:
+                unexpected_keys.append(prefix + k)
+        self._host_sd = {k: sub[k] for k in self.shapes}
+        if self.W is not None:
+            self.pack_weights(self.W["device"])
+
+    def load_weights(self, sd, device):
+        """sd: UNetModel.state_dict()-style mapping (reference key names). Packs to kernel-native fp16 layouts."""
+        for k, shape in self.shapes.items():
+            assert k in sd, f"missing key {k}"
+            assert tuple(sd[k].shape) == tuple(shape), (k, tuple(sd[k].shape), shape)
+        self._host_sd = {k: sd[k] for k in self.shapes}
+        self.pack_weights(torch.device(device))
+        return self
+
+    def _apply(self, fn, *a, **k):  # .cuda()/.to(device) triggers packing, like moving an nn.Module's parameters
+        r = super()._apply(fn, *a, **k)
+        probe = fn(torch.empty(0))
+        if probe.is_cuda and getattr(self, "_host_sd", None) is not None and (self.W is None or self.W["device"] != probe.device):
+            self.pack_weights(probe.device)
+        return r
+
+    @torch.no_grad()
+    def pack_weights(self, device):
+        sd = {k: v.detach().to(device=device, dtype=torch.float32) for k, v in self._host_sd.items()}
+        W = {"device": device}
+        f32 = lambda k: sd[k].contiguous()
+        f16 = lambda k: sd[k].half().contiguous()
+        heads = self.num_heads
+        mc = self.model_channels
+        W["te0_w"], W["te0_b"] = f16("time_embed.0.weight"), f32("time_embed.0.bias")
+        W["te2_w"], W["te2_b"] = f16("time_embed.2.weight"), f32("time_embed.2.bias")
+        emb_w, emb_b, emb_off = [], [], {}
+        off = 0
+
+        def pack_res(pre, a):
+            nonlocal off
+            r = {"cin": a["cin"], "cout": a["cout"]}
+            r["gn1"] = (f32(pre + ".in_layers.0.weight"), f32(pre + ".in_layers.0.bias"))
+            r["w1"], r["b1"] = _pack_conv3(sd[pre + ".in_layers.2.weight"]), f32(pre + ".in_layers.2.bias")
+            r["gn2"] = (f32(pre + ".out_layers.0.weight"), f32(pre + ".out_layers.0.bias"))
+            r["w2"], r["b2"] = _pack_conv3(sd[pre + ".out_layers.3.weight"]), f32(pre + ".out_layers.3.bias")
+            if a["cin"] != a["cout"]:
+                r["ws"] = sd[pre + ".skip_connection.weight"].reshape(a["cout"], a["cin"]).half().contiguous()
+                r["bs"] = f32(pre + ".skip_connection.bias")
+            emb_w.append(sd[pre + ".emb_layers.1.weight"].half())
+            emb_b.append(sd[pre + ".emb_layers.1.bias"])
+            r["film_off"] = off
+            off += a["cout"]
+            return r
+
+        def pack_st(pre, a):
+            ch, d = a["ch"], a["dhead"]
+            dp = _dpad(d)
+            tb = pre + ".transformer_blocks.0"
+            s = {"ch": ch, "d": d, "dpad": dp, "heads": heads}
+            s["gn"] = (f32(pre + ".norm.weight"), f32(pre + ".norm.bias"))
+            s["w_in"], s["b_in"] = sd[pre + ".proj_in.weight"].reshape(ch, ch).half().contiguous(), f32(pre + ".proj_in.bias")
+            s["w_out"], s["b_out"] = sd[pre + ".proj_out.weight"].reshape(ch, ch).half().contiguous(), f32(pre + ".proj_out.bias")
+            for i in (1, 2, 3):
+                s[f"ln{i}"] = (f32(f"{tb}.norm{i}.weight"), f32(f"{tb}.norm{i}.bias"))
+            s["w_qk1"] = torch.cat([_pack_heads(sd[tb + ".attn1.to_q.weight"], heads, d, dp),
+                                    _pack_heads(sd[tb + ".attn1.to_k.weight"], heads, d, dp)], 0).contiguous()
+            s["w_v1"] = _pack_heads(sd[tb + ".attn1.to_v.weight"], heads, d, dp)
+            s["w_o1"], s["b_o1"] = f16(tb + ".attn1.to_out.0.weight"), f32(tb + ".attn1.to_out.0.bias")
+            s["w_q2"] = _pack_heads(sd[tb + ".attn2.to_q.weight"], heads, d, dp)
+            s["w_kv2"] = torch.cat([_pack_heads(sd[tb + ".attn2.to_k.weight"], heads, d, dp),
+                                    _pack_heads(sd[tb + ".attn2.to_v.weight"], heads, d, dp)], 0).contiguous()
+            s["w_o2"], s["b_o2"] = f16(tb + ".attn2.to_out.0.weight"), f32(tb + ".attn2.to_out.0.bias")
+            s["w_ff1"], s["b_ff1"] = _pack_geglu(sd[tb + ".ff.net.0.proj.weight"], sd[tb + ".ff.net.0.proj.bias"])
+            s["w_ff2"], s["b_ff2"] = f16(tb + ".ff.net.2.weight"), f32(tb + ".ff.net.2.bias")
+            return s
+
+        def pack_layers(layers):
+            out = []
+            for kind, pre, a in layers:
+                if kind == "conv_in":
+                    out.append((kind, {"w": _pack_conv3_padk(sd[pre + ".weight"], 64), "b": f32(pre + ".bias"),
+                                       "cout": a["cout"]}))
+                elif kind == "res":
+                    out.append((kind, pack_res(pre, a)))
+                elif kind == "st":
+                    out.append((kind, pack_st(pre, a)))
+                elif kind == "down":
+                    out.append((kind, {"w": _pack_conv3(sd[pre + ".op.weight"]), "b": f32(pre + ".op.bias"), "ch": a["ch"]}))
+                elif kind == "up":
+                    out.append((kind, {"w": _pack_conv3(sd[pre + ".conv.weight"]), "b": f32(pre + ".conv.bias"), "ch": a["ch"]}))
+            return out
+
+        W["input"] = [pack_layers(l) for l in self.plan["input"]]
+        W["middle"] = pack_layers(self.plan["middle"])
+        W["output"] = [pack_layers(l) for l in self.plan["output"]]
+        W["gn_out"] = (f32("out.0.weight"), f32("out.0.bias"))
+        W["w_out"], W["b_out"] = _pack_conv3(sd["out.2.weight"]), f32("out.2.bias")
+        W["emb_w"] = torch.cat(emb_w, 0).contiguous()
+        W["emb_b"] = torch.cat(emb_b, 0).float().contiguous()
+        W["st_list"] = [p for grp in W["input"] + [W["middle"]] + W["output"] for k, p in grp if k == "st"]
+        self.W = W
+        self._ctx_key = None
+        self._graphs = {}
+
+    # ------------------------------------------------------------------ blocks
+    def _film(self, t):
+        """time_embed MLP + all 22 emb_layers in three weight-streaming launches (fp32 activations)."""
+        W = self.W
+        te = ops.timestep_embedding_f32(t, self.model_channels)
+        h = ops.linear_small(te, W["te0_w"], W["te0_b"], act=ACT_SILU)
+        # ResBlocks only ever consume SiLU(emb) (openaimodel.py:217-218), so apply it in this epilogue
+        h = ops.linear_small(h, W["te2_w"], W["te2_b"], act=ACT_SILU)
+        return ops.linear_small(h, W["emb_w"], W["emb_b"])          # [N, sum(Cout)] fp32
+
+    def _res(self, r, h, skip, film):
+        """ResBlock._forward (openaimodel.py:255-275); `skip` is the UNet skip tensor concatenated along C."""
+        nb, H, Wd, _ = h.shape
+        hn, raw = ops.groupnorm(h, *r["gn1"], x1=skip, eps=1e-5, silu=True, want_raw="ws" in r)
+        fv = film[:, r["film_off"]: r["film_off"] + r["cout"]]
+        _, h1 = ops.gemm(hn, r["w1"], taps=9, bias=r["b1"], film=fv, want_f32=True, splits=-1)
+        h1 = h1.view(nb, H, Wd, r["cout"])
+        hn2, _ = ops.groupnorm(h1, *r["gn2"], eps=1e-5, silu=True)
+        if "ws" in r:
+            _, res = ops.gemm(raw, r["ws"], bias=r["bs"], want_f32=True, splits=-1)
+        else:
+            assert skip is None
+            res = h.view(-1, r["cout"])
+        _, out = ops.gemm(hn2, r["w2"], taps=9, bias=r["b2"], residual=res, want_f32=True, splits=-1)
+        return out.view(nb, H, Wd, r["cout"])
+
+    def _st(self, s, x, kv):
+        """SpatialTransformer.forward (attention.py:250-261) with one BasicTransformerBlock (:211-215)."""
+        nb, H, Wd, ch = x.shape
+        ntok = H * Wd
+        heads, d, dp = s["heads"], s["d"], s["dpad"]
+        hd = heads * dp
+        scale = d ** -0.5
+        xn, _ = ops.groupnorm(x, *s["gn"], eps=1e-6, silu=False)
+        _, t0 = ops.gemm(xn, s["w_in"], bias=s["b_in"], want_f32=True, splits=-1)          # tokens [M, ch] fp32
+        # --- self attention
+        y = ops.layernorm(t0, *s["ln1"])
+        qk, _ = ops.gemm(y, s["w_qk1"], want_f16=True)                                     # [M, 2*hd]
+        qk3 = qk.view(nb, ntok, 2 * hd)
+        if ntok % 8 == 0:
+            # V^T straight out of the tensor cores by swapping the operand roles: [hd, M] = Wv . y^T
+            vt, _ = ops.gemm(s["w_v1"], y, want_f16=True)
+            vt3 = vt.view(hd, nb, ntok).permute(1, 0, 2)                                   # [nb, hd, ntok] (strided view)
+        else:  # TMA needs 16-byte aligned strides: tiny token counts go through an explicit transpose
+            v, _ = ops.gemm(y, s["w_v1"], want_f16=True)
+            vt3 = ops.transpose_f16(v.view(nb, ntok, hd))
+        o = ops.attention(qk3[:, :, :hd], qk3[:, :, hd:], vt3, heads=heads, d=d, dpad=dp, nq=ntok, nkv=ntok, scale=scale)
+        _, t1 = ops.gemm(o.view(-1, ch), s["w_o1"], bias=s["b_o1"], residual=t0, want_f32=True, splits=-1)
+        # --- cross attention (K / V^T of the context are precomputed per prompt)
+        y = ops.layernorm(t1, *s["ln2"])
+        q, _ = ops.gemm(y, s["w_q2"], want_f16=True)
+        k2, vt2, nkv = kv
+        o = ops.attention(q.view(nb, ntok, hd), k2, vt2, heads=heads, d=d, dpad=dp, nq=ntok, nkv=nkv, scale=scale)
+        _, t2 = ops.gemm(o.view(-1, ch), s["w_o2"], bias=s["b_o2"], residual=t1, want_f32=True, splits=-1)
+        # --- GEGLU feed-forward
+        y = ops.layernorm(t2, *s["ln3"])
+        g, _ = ops.gemm(y, s["w_ff1"], bias=s["b_ff1"], act=ACT_GEGLU, want_f16=True)
+        t3, _ = ops.gemm(g, s["w_ff2"], bias=s["b_ff2"], residual=t2, want_f16=True, splits=-1)
+        _, out = ops.gemm(t3, s["w_out"], bias=s["b_out"], residual=x.view(-1, ch), want_f32=True, splits=-1)
+        return out.view(nb, H, Wd, ch)
+
+    def context_kv(self, context):
+        """Cross-attention K and V^T for all SpatialTransformers (x/t independent: once per prompt)."""
+        nb, nkv, cd = context.shape
+        ctx16 = ops.cast_f16(context.contiguous().float().view(nb * nkv, cd))
+        out = []
+        for s in self.W["st_list"]:
+            hd = s["heads"] * s["dpad"]
+            kvp, _ = ops.gemm(ctx16, s["w_kv2"], want_f16=True)                            # [nb*nkv, 2*hd]
+            kv3 = kvp.view(nb, nkv, 2 * hd)
+            v = kv3[:, :, hd:].contiguous()
+            out.append((kv3[:, :, :hd], ops.transpose_f16(v), nkv))
+        return out
+
+    def set_context(self, context):
+        """Cache the cross-attention K/V for `context` ([uncond; cond] batch); forward() reuses it while the same
+        tensor (same storage, same version) is passed."""
+        self._ctx_kv = self.context_kv(context)
+        self._ctx_key = (context.data_ptr(), context._version, tuple(context.shape))
+        return self._ctx_kv
+
+    def _run_layers(self, layers, h, skip, film, kvs, st_idx):
+        for kind, p in layers:
+            if kind == "res":
+                h = self._res(p, h, skip, film)
+                skip = None
+            elif kind == "st":
+                h = self._st(p, h, kvs[st_idx[0]])
+                st_idx[0] += 1
+            elif kind == "down":
+                nb, H, Wd, c = h.shape
+                col = ops.im2col3x3(h, 2, 1, H // 2, Wd // 2, 9 * c)
+                _, o = ops.gemm(col, p["w"], bias=p["b"], want_f32=True, splits=-1)
+                h = o.view(nb, H // 2, Wd // 2, c)
+            elif kind == "up":
+                nb, H, Wd, c = h.shape
+                up = ops.upsample2x(h)
+                _, o = ops.gemm(up, p["w"], taps=9, bias=p["b"], want_f32=True, splits=-1)
+                h = o.view(nb, 2 * H, 2 * Wd, c)
+            elif kind == "conv_in":
+                nb, H, Wd, c = h.shape
+                col = ops.im2col3x3(h, 1, 1, H, Wd, 64)
+                _, o = ops.gemm(col, p["w"], bias=p["b"], want_f32=True)
+                h = o.view(nb, H, Wd, p["cout"])
+        return h
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward(self, x, timesteps=None, context=None, y=None, **kwargs):
+        assert y is None, "must specify y if and only if the model is class-conditional"
+        assert self.W is not None, "weights not loaded (load_state_dict / load_weights, then .cuda())"
+        if not x.is_cuda:
+            raise RuntimeError("sdb200.UNetModel runs on CUDA (sm_100a) only; there is no CPU fallback")
+        assert x.dim() == 4 and x.shape[1] == self.in_channels
+        assert context is not None and context.shape[0] == x.shape[0] and context.shape[2] == self.context_dim
+        nb, _, H, Wd = x.shape
+        lv = len(self.cfg["channel_mult"]) - 1
+        assert H % (1 << lv) == 0 and Wd % (1 << lv) == 0, "latent size must be divisible by 2^(levels-1)"
+        key = (context.data_ptr(), context._version, tuple(context.shape))
+        kvs = self._ctx_kv if key == self._ctx_key else self.context_kv(context)
+        t = timesteps.to(torch.float32).contiguous()
+        film = self._film(t)
+        h, _ = ops.nchw_to_nhwc(x.contiguous().float())
+        W = self.W
+        hs = []
+        st_idx = [0]
+        for layers in W["input"]:
+            h = self._run_layers(layers, h, None, film, kvs, st_idx)
+            hs.append(h)
+        h = self._run_layers(W["middle"], h, None, film, kvs, st_idx)
+        for layers in W["output"]:
+            h = self._run_layers(layers, h, hs.pop(), film, kvs, st_idx)
+        hn, _ = ops.groupnorm(h, *W["gn_out"], eps=1e-5, silu=True)
+        _, o = ops.gemm(hn, W["w_out"], taps=9, bias=W["b_out"], want_f32=True)
+        eps = ops.nhwc_to_nchw(o.view(nb, H, Wd, self.out_channels))
+        return eps.to(x.dtype)

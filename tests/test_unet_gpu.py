@@ -1,0 +1,71 @@
+"""eps parity of the B200 UNet against the reference's outputs (golden fixtures from the unmodified reference)
+and against the oracle on fresh seeded inputs. Tolerance: north_star's 1e-3 rel-L2 (fp16 operands, fp32 accumulate)."""
+import pytest
+import torch
+
+from helpers import CFGS, golden, rel_l2, weights
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+TOL = 1e-3
+_models = {}
+
+
+def _model(tag, seed, dev):
+    import sdb200
+    key = (tag, seed)
+    if key not in _models:
+        m = sdb200.UNetModel(**CFGS["unet"][tag])
+        m.load_weights(weights("unet", tag, seed), dev)
+        _models[key] = m
+    return _models[key]
+
+
+@pytest.mark.parametrize("idx", range(5))
+def test_unet_eps_vs_reference_golden(cuda_dev, idx):
+    case = golden("unet.pt")[idx]
+    m = _model(case["cfg"], case["seed"], cuda_dev)
+    eps = m(case["x"].to(cuda_dev), case["t"].to(cuda_dev), context=case["ctx"].to(cuda_dev))
+    torch.cuda.synchronize()
+    assert eps.shape == case["eps"].shape and eps.dtype == torch.float32
+    err = rel_l2(eps, case["eps"])
+    print(f"unet {case['cfg']} {tuple(case['x'].shape)} rel-L2 {err:.3e}")
+    assert err < TOL, err
+
+
+def test_unet_eps_vs_oracle_fresh_inputs(cuda_dev):
+    import ldm_oracle as O
+    sd = weights("unet", "tiny", 11)
+    m = _model("tiny", 11, cuda_dev)
+    g = torch.Generator().manual_seed(77)
+    for shape, ts in [((2, 4, 16, 16), [721, 41]), ((1, 4, 8, 8), [1]), ((5, 4, 24, 24), [981, 500, 300, 21, 1])]:
+        x = torch.randn(shape, generator=g)
+        t = torch.tensor(ts)
+        ctx = torch.randn(shape[0], 77, 64, generator=g)
+        ref = O.unet_forward(sd, x, t, ctx, num_heads=2)
+        eps = m(x.to(cuda_dev), t.to(cuda_dev), context=ctx.to(cuda_dev))
+        assert rel_l2(eps, ref) < TOL, (shape, rel_l2(eps, ref))
+
+
+def test_unet_context_cache_and_determinism(cuda_dev):
+    case = golden("unet.pt")[0]
+    m = _model(case["cfg"], case["seed"], cuda_dev)
+    x, t, ctx = case["x"].to(cuda_dev), case["t"].to(cuda_dev), case["ctx"].to(cuda_dev)
+    a = m(x, t, context=ctx)
+    m.set_context(ctx)
+    b = m(x, t, context=ctx)
+    c = m(x, t, context=ctx)
+    assert torch.equal(a, b) and torch.equal(b, c)
+
+
+def test_unet_rejects_bad_arguments(cuda_dev):
+    import sdb200
+    m = _model("tiny", 11, cuda_dev)
+    with pytest.raises(AssertionError):
+        m(torch.zeros(1, 4, 16, 16, device=cuda_dev), torch.zeros(1, device=cuda_dev), context=None)
+    with pytest.raises(AssertionError):
+        m(torch.zeros(1, 4, 16, 16, device=cuda_dev), torch.zeros(1, device=cuda_dev),
+          context=torch.zeros(1, 77, 64, device=cuda_dev), y=torch.zeros(1, device=cuda_dev))
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 4, 16, 16), torch.zeros(1), context=torch.zeros(1, 77, 64))
+    with pytest.raises(NotImplementedError):
+        sdb200.UNetModel(**{**CFGS["unet"]["tiny"], "use_scale_shift_norm": True})
