@@ -286,25 +286,27 @@ def _is_norm_key(k):
     return (len(parts) >= 3 and parts[-3] in ("in_layers", "out_layers") and leaf == "0") or k.startswith("out.0.")
 
 
-def random_state_dict(shapes, seed, prefix=""):
-    """Seeded synthetic weights (CPU fp32), independent of module construction order.
+def random_state_dict(shapes, seed, prefix="", device="cpu"):
+    """Seeded synthetic weights (fp32), independent of module construction order. device="cpu" gives the values the
+    golden fixtures were made with; a CUDA device draws from the device generator (fast; used by the benchmark).
 
     weights ~ N(0, 1/fan_in); norm gains 1 + 0.1 N(0,1); biases and norm shifts 0.1 N(0,1) (embeddings N(0, 0.02^2)
     as CLIP). Each tensor gets its own generator seeded from (seed, index) so a subset can be regenerated.
     """
     sd = OrderedDict()
     for i, (k, shape) in enumerate(shapes.items()):
-        g = torch.Generator().manual_seed(seed * 1000003 + i)
+        g = torch.Generator(device=device).manual_seed(seed * 1000003 + i)
+        rn = lambda: torch.randn(shape, generator=g, device=device)
         if k.endswith(".bias"):
-            t = 0.1 * torch.randn(shape, generator=g)
+            t = 0.1 * rn()
         elif _is_norm_key(k):
-            t = 1.0 + 0.1 * torch.randn(shape, generator=g)
+            t = 1.0 + 0.1 * rn()
         elif "embedding" in k:
-            t = 0.02 * torch.randn(shape, generator=g)
+            t = 0.02 * rn()
         else:
             fan_in = 1
             for s in shape[1:]:
                 fan_in *= s
-            t = torch.randn(shape, generator=g) * fan_in ** -0.5
+            t = rn() * fan_in ** -0.5
         sd[prefix + k] = t
     return sd

@@ -99,7 +99,7 @@ class LatentDiffusion(nn.Module):
         enc = getattr(self.cond_stage_model, "encode", None)
         if callable(enc):
             c = enc(c)
-            if hasattr(c, "mode"):
+            if not torch.is_tensor(c) and hasattr(c, "mode"):   # DiagonalGaussianDistribution (ddpm.py:555-556)
                 c = c.mode()
         else:
             c = self.cond_stage_model(c)

@@ -13,7 +13,20 @@ import torch
 from . import lib as _l
 from .lib import ACT_GEGLU, ACT_NONE, ACT_QUICK_GELU, ACT_SILU, AttnDesc, GemmDesc  # noqa: F401
 
-LAUNCHES = 0  # kernels enqueued through this module (bench.py's gpu_launches claim)
+LAUNCHES = 0        # op calls made through this module
+_GRAPH_LAUNCHES = 0  # kernels replayed from CUDA graphs (counted at capture time, added per replay)
+PROFILE = None      # when a list: gemm()/attention() append (kind, flops, start_event, end_event)
+
+
+def launch_count():
+    """Kernels launched from libsdb200.so: direct launches (counted in C) + kernels replayed inside CUDA graphs."""
+    return int(_l.load().sdb_launch_count()) + _GRAPH_LAUNCHES
+
+
+def add_graph_launches(n):
+    global _GRAPH_LAUNCHES
+    _GRAPH_LAUNCHES += int(n)
+
 
 
 def _ptr(t):
@@ -90,7 +103,13 @@ def gemm(a0, b, *, a1=None, nb=None, h=None, w=None, taps=1, bias=None, film=Non
         assert splits == -1 or workspace.numel() >= splits * M * n
         d.workspace = _ptr(workspace)
         d.workspace_floats = workspace.numel()
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     _l.check(_l.load().sdb_gemm(C.byref(d), _stream()), "sdb_gemm")
+    if PROFILE is not None:
+        e1.record()
+        PROFILE.append(("gemm", 2.0 * M * n * b.shape[1], e0, e1, (M, n, b.shape[1], taps)))
     _count(2 if splits and splits > 1 else 1)
     return out_f16, out_f32
 
@@ -121,7 +140,13 @@ def attention(q, k, vt, *, heads, d, dpad, nq, nkv, scale, causal=False, out=Non
     a.q_batch_stride, a.k_batch_stride = q.stride(0), k.stride(0)
     a.vt_batch_stride, a.o_batch_stride = vt.stride(0), out.stride(0)
     a.scale, a.causal = scale, 1 if causal else 0
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     _l.check(_l.load().sdb_attention(C.byref(a), _stream()), "sdb_attention")
+    if PROFILE is not None:
+        e1.record()
+        PROFILE.append(("attention", 4.0 * B * heads * nq * nkv * d, e0, e1, (B, heads, nq, nkv, d)))
     _count()
     return out
 
@@ -226,13 +251,15 @@ def silu_f16(x):
     return out
 
 
-def transpose_f16(x, ldo=None):
+def transpose_f16(x, ldo=None, out=None):
     """x fp16 [B, rows, cols] -> [B, cols, ldo] (rows valid, ldo >= rows, multiple of 8 for TMA)."""
     _chk16(x, "x")
     B, rows, cols = x.shape
     if ldo is None:
         ldo = (rows + 7) // 8 * 8
-    out = torch.empty((B, cols, ldo), dtype=torch.float16, device=x.device)  # pad columns are never read
+    if out is None:
+        out = torch.empty((B, cols, ldo), dtype=torch.float16, device=x.device)  # pad columns are never read
+    assert out.shape == (B, cols, ldo) and out.is_contiguous()
     _l.check(_l.load().sdb_transpose_f16(_ptr(x), B, rows, cols, cols, _ptr(out), ldo, _stream()),
              "sdb_transpose_f16")
     _count()

@@ -87,7 +87,9 @@ class UNetModel(nn.Module):
         self.W = None           # packed weights (device)
         self._ctx_key = None
         self._ctx_kv = None
+        self._kv_static = {}
         self._graphs = {}
+        self.use_cuda_graph = False   # replay one captured graph per UNet evaluation (set by the pipeline / bench)
 
     # ------------------------------------------------------------------ weights
     def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
@@ -164,8 +166,8 @@ class UNetModel(nn.Module):
             s["w_v1"] = _pack_heads(sd[tb + ".attn1.to_v.weight"], heads, d, dp)
             s["w_o1"], s["b_o1"] = f16(tb + ".attn1.to_out.0.weight"), f32(tb + ".attn1.to_out.0.bias")
             s["w_q2"] = _pack_heads(sd[tb + ".attn2.to_q.weight"], heads, d, dp)
-            s["w_kv2"] = torch.cat([_pack_heads(sd[tb + ".attn2.to_k.weight"], heads, d, dp),
-                                    _pack_heads(sd[tb + ".attn2.to_v.weight"], heads, d, dp)], 0).contiguous()
+            s["w_k2"] = _pack_heads(sd[tb + ".attn2.to_k.weight"], heads, d, dp)
+            s["w_v2"] = _pack_heads(sd[tb + ".attn2.to_v.weight"], heads, d, dp)
             s["w_o2"], s["b_o2"] = f16(tb + ".attn2.to_out.0.weight"), f32(tb + ".attn2.to_out.0.bias")
             s["w_ff1"], s["b_ff1"] = _pack_geglu(sd[tb + ".ff.net.0.proj.weight"], sd[tb + ".ff.net.0.proj.bias"])
             s["w_ff2"], s["b_ff2"] = f16(tb + ".ff.net.2.weight"), f32(tb + ".ff.net.2.bias")
@@ -197,6 +199,7 @@ class UNetModel(nn.Module):
         W["st_list"] = [p for grp in W["input"] + [W["middle"]] + W["output"] for k, p in grp if k == "st"]
         self.W = W
         self._ctx_key = None
+        self._kv_static = {}
         self._graphs = {}
 
     # ------------------------------------------------------------------ blocks
@@ -260,23 +263,31 @@ class UNetModel(nn.Module):
         _, out = ops.gemm(t3, s["w_out"], bias=s["b_out"], residual=x.view(-1, ch), want_f32=True, splits=-1)
         return out.view(nb, H, Wd, ch)
 
-    def context_kv(self, context):
-        """Cross-attention K and V^T for all SpatialTransformers (x/t independent: once per prompt)."""
+    def context_kv(self, context, static=False):
+        """Cross-attention K and V^T for all SpatialTransformers (x/t independent: once per prompt).
+        static=True writes into persistent per-shape buffers so captured CUDA graphs stay valid across prompts."""
         nb, nkv, cd = context.shape
         ctx16 = ops.cast_f16(context.contiguous().float().view(nb * nkv, cd))
+        bufs = self._kv_static.setdefault((nb, nkv), {}) if static else {}
+        ld = (nkv + 7) // 8 * 8
         out = []
-        for s in self.W["st_list"]:
+        for i, s in enumerate(self.W["st_list"]):
             hd = s["heads"] * s["dpad"]
-            kvp, _ = ops.gemm(ctx16, s["w_kv2"], want_f16=True)                            # [nb*nkv, 2*hd]
-            kv3 = kvp.view(nb, nkv, 2 * hd)
-            v = kv3[:, :, hd:].contiguous()
-            out.append((kv3[:, :, :hd], ops.transpose_f16(v), nkv))
+            if i not in bufs:
+                bufs[i] = (torch.empty((nb * nkv, hd), dtype=torch.float16, device=context.device),
+                           torch.empty((nb * nkv, hd), dtype=torch.float16, device=context.device),
+                           torch.empty((nb, hd, ld), dtype=torch.float16, device=context.device))
+            kb, vb, vtb = bufs[i]
+            ops.gemm(ctx16, s["w_k2"], out_f16=kb)
+            ops.gemm(ctx16, s["w_v2"], out_f16=vb)
+            ops.transpose_f16(vb.view(nb, nkv, hd), out=vtb)
+            out.append((kb.view(nb, nkv, hd), vtb, nkv))
         return out
 
     def set_context(self, context):
         """Cache the cross-attention K/V for `context` ([uncond; cond] batch); forward() reuses it while the same
         tensor (same storage, same version) is passed."""
-        self._ctx_kv = self.context_kv(context)
+        self._ctx_kv = self.context_kv(context, static=True)
         self._ctx_key = (context.data_ptr(), context._version, tuple(context.shape))
         return self._ctx_kv
 
@@ -306,6 +317,44 @@ class UNetModel(nn.Module):
         return h
 
     # ------------------------------------------------------------------ forward
+    def _forward_impl(self, x, t, kvs):
+        """x NCHW fp32, t fp32 [nb], kvs from context_kv -> eps NCHW fp32. Pure kernel sequence (graph-capturable)."""
+        nb, _, H, Wd = x.shape
+        film = self._film(t)
+        h, _ = ops.nchw_to_nhwc(x)
+        W = self.W
+        hs = []
+        st_idx = [0]
+        for layers in W["input"]:
+            h = self._run_layers(layers, h, None, film, kvs, st_idx)
+            hs.append(h)
+        h = self._run_layers(W["middle"], h, None, film, kvs, st_idx)
+        for layers in W["output"]:
+            h = self._run_layers(layers, h, hs.pop(), film, kvs, st_idx)
+        hn, _ = ops.groupnorm(h, *W["gn_out"], eps=1e-5, silu=True)
+        _, o = ops.gemm(hn, W["w_out"], taps=9, bias=W["b_out"], want_f32=True)
+        return ops.nhwc_to_nchw(o.view(nb, H, Wd, self.out_channels))
+
+    def _graph_for(self, shape, kvs):
+        """Capture one UNet evaluation (~330 kernels) as a CUDA graph with static x / t / eps / K,V buffers."""
+        g = self._graphs.get(shape)
+        if g is None:
+            dev = self.W["device"]
+            sx = torch.zeros(shape, dtype=torch.float32, device=dev)
+            st = torch.zeros((shape[0],), dtype=torch.float32, device=dev)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):      # warm-up outside capture: cudaFuncSetAttribute, allocator pools
+                self._forward_impl(sx, st, kvs)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            n0 = ops.launch_count()
+            with torch.cuda.graph(graph):
+                out = self._forward_impl(sx, st, kvs)
+            g = {"graph": graph, "x": sx, "t": st, "out": out, "launches": ops.launch_count() - n0, "kvs": kvs}
+            self._graphs[shape] = g
+        return g
+
     @torch.no_grad()
     def forward(self, x, timesteps=None, context=None, y=None, **kwargs):
         assert y is None, "must specify y if and only if the model is class-conditional"
@@ -318,20 +367,18 @@ class UNetModel(nn.Module):
         lv = len(self.cfg["channel_mult"]) - 1
         assert H % (1 << lv) == 0 and Wd % (1 << lv) == 0, "latent size must be divisible by 2^(levels-1)"
         key = (context.data_ptr(), context._version, tuple(context.shape))
+        if self.use_cuda_graph:
+            if key != self._ctx_key:
+                self.set_context(context)
+            g = self._graph_for(tuple(x.shape), self._ctx_kv)
+            assert g["kvs"] is self._ctx_kv or all(a[0].data_ptr() == b[0].data_ptr() for a, b in zip(g["kvs"], self._ctx_kv))
+            if x.data_ptr() != g["x"].data_ptr():
+                g["x"].copy_(x)
+            g["t"].copy_(timesteps)
+            g["graph"].replay()
+            ops.add_graph_launches(g["launches"])
+            return g["out"]
         kvs = self._ctx_kv if key == self._ctx_key else self.context_kv(context)
         t = timesteps.to(torch.float32).contiguous()
-        film = self._film(t)
-        h, _ = ops.nchw_to_nhwc(x.contiguous().float())
-        W = self.W
-        hs = []
-        st_idx = [0]
-        for layers in W["input"]:
-            h = self._run_layers(layers, h, None, film, kvs, st_idx)
-            hs.append(h)
-        h = self._run_layers(W["middle"], h, None, film, kvs, st_idx)
-        for layers in W["output"]:
-            h = self._run_layers(layers, h, hs.pop(), film, kvs, st_idx)
-        hn, _ = ops.groupnorm(h, *W["gn_out"], eps=1e-5, silu=True)
-        _, o = ops.gemm(hn, W["w_out"], taps=9, bias=W["b_out"], want_f32=True)
-        eps = ops.nhwc_to_nchw(o.view(nb, H, Wd, self.out_channels))
+        eps = self._forward_impl(x.contiguous().float(), t, kvs)
         return eps.to(x.dtype)

@@ -197,8 +197,9 @@ class AutoencoderKL(nn.Module):
 
     # ------------------------------------------------------------------ public API
     @torch.no_grad()
-    def decode(self, z, scale=1.0):
-        """AutoencoderKL.decode (autoencoder.py:330-333) on z*scale; NCHW fp32 in / out."""
+    def decode(self, z, scale=1.0, nhwc=False):
+        """AutoencoderKL.decode (autoencoder.py:330-333) on z*scale; NCHW fp32 in / out (nhwc=True keeps the
+        kernels' native NHWC output, which is what the image writer wants: txt2img.py:322)."""
         assert self.W is not None and z.is_cuda, "sdb200.AutoencoderKL runs on CUDA only (no CPU fallback)"
         W, D = self.W, self.W["decoder"]
         zh, _ = ops.nchw_to_nhwc(z.contiguous().float())
@@ -214,7 +215,7 @@ class AutoencoderKL(nn.Module):
                 h = self._conv3(lvl["resample"], x16=ops.upsample2x(h))
         hn, _ = ops.groupnorm(h, *D["gn_out"], eps=1e-6, silu=True)
         out = self._conv3(D["conv_out"], x16=hn)
-        return ops.nhwc_to_nchw(out)
+        return out if nhwc else ops.nhwc_to_nchw(out)
 
     @torch.no_grad()
     def encode(self, x):
