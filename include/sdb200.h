@@ -41,16 +41,19 @@ enum {
  *   v         = alpha * acc + bias[n] + film[m / rows_per_sample, n] + residual[m, n]
  *   out       = act(v)   written as fp16 and/or fp32, row stride ldo
  *
- * A is one or two NHWC fp16 tensors concatenated along channels (the UNet skip concat,
- * openaimodel.py:736, folded into the K loop). taps = 1: plain [rows, C] matrix (nn.Linear, 1x1 conv:
+ * A is one to four NHWC fp16 tensors concatenated along channels: the UNet skip concat (openaimodel.py:736) folded
+ * into the K loop, or the hi/lo fp16 halves of one fp32 activation ([A_hi | A_lo | A_hi] against [W_hi | W_hi | W_lo]
+ * recovers ~fp32 operand precision for the few 1x1 convs that act on the raw residual stream). taps = 1: plain [rows, C] matrix (nn.Linear, 1x1 conv:
  * attention.py:161-168,233-248; openaimodel.py:241). taps = 9: 3x3 conv, stride 1, zero pad 1
  * (openaimodel.py:204,230,519,685; model.py:44-50,94-118) with B laid out [n, 9*(c0+c1)], k = tap*(c0+c1)+c.
- * c0 and c1 must be multiples of 64.
+ * All channel counts must be multiples of 64.
  */
 typedef struct sdb_gemm_desc {
   const void* a0;        /* fp16 [nb, h, w, c0] */
-  const void* a1;        /* fp16 [nb, h, w, c1] or NULL */
-  int32_t c0, c1;
+  const void* a1;        /* fp16 [nb, h, w, c1] or NULL; further sources a2, a3 likewise (contiguous from a0) */
+  const void* a2;
+  const void* a3;
+  int32_t c0, c1, c2, c3;
   int32_t nb, h, w;      /* rows M = nb*h*w */
   int32_t taps;          /* 1 or 9 */
   const void* b;         /* fp16 [n, taps*(c0+c1)] */
@@ -64,6 +67,7 @@ typedef struct sdb_gemm_desc {
   int32_t ldr;
   int32_t act;           /* SDB_ACT_* */
   void* out_f16;         /* fp16 [M, ldo] or NULL */
+  void* out_f16_lo;      /* optional fp16 [M, ldo]: fp16(v - float(out_f16)), the low half of a hi/lo operand split */
   float* out_f32;        /* fp32 [M, ldo] or NULL */
   int32_t ldo;           /* 0 = dense (n, or n/2 for GEGLU) */
   int32_t block_n;       /* 0 = auto; else one of 32,64,128,160,256 */
@@ -108,6 +112,8 @@ int sdb_attention(const sdb_attn_desc* d, sdb_stream_t stream);
  */
 int sdb_groupnorm(const float* x0, const float* x1, int32_t c0, int32_t c1, int32_t nb, int32_t hw, int32_t groups,
                   const float* gamma, const float* beta, float eps, int32_t silu, void* out_f16, void* raw_f16,
+                  void* out_lo_f16 /* optional low half of the normalised output (hi/lo split) */,
+                  void* raw_lo_f16 /* optional low half of the raw cast */,
                   void* stats_ws /* 2*nb*groups doubles, zeroed by the call */, sdb_stream_t stream);
 
 /* LayerNorm over the last dim of fp32 [rows, c] -> fp16 (attention.py:203-205, eps 1e-5). */

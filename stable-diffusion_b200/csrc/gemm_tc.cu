@@ -1,12 +1,16 @@
-// tcgen05 GEMM / implicit-GEMM 3x3 convolution for sm_100a.
+// tcgen05 GEMM / implicit-GEMM 3x3 convolution for sm_100a — persistent, warp-specialised.
 //
-//   warp 0      : TMA producer (one elected lane) — A tile [128 rows x 64 ch] via a 4-D NHWC tensor map
-//                 (3x3 taps are shifted boxes; out-of-image reads are zero-filled by TMA = conv padding),
-//                 B tile [BN x 64] from the K-major weight matrix.
-//   warp 1      : TMEM allocation + single-thread tcgen05.mma issue (M=128, N=BN, K=16 per instruction),
-//                 tcgen05.commit releases smem stages and finally signals the epilogue.
-//   warps 2..5  : epilogue — tcgen05.ld accumulator rows (one row per thread), fused
-//                 alpha/bias/FiLM/residual/activation, fp16 and/or fp32 stores.
+//   grid        : min(#tiles, #SMs) persistent CTAs, static round-robin tile schedule (M fastest, so CTAs running
+//                 side by side read the same weight tile from L2)
+//   warp 0      : TMA producer (one elected lane) — A tile [128 rows x 64 ch] via 4-D NHWC tensor maps (3x3 taps are
+//                 shifted boxes; out-of-image reads are zero-filled by TMA = conv padding; up to four A sources are
+//                 concatenated along K: UNet skip concat, or hi/lo fp16 splits of one fp32 activation),
+//                 B tile [BN x 64] from the K-major weight matrix. STAGES-deep mbarrier ring that runs across tiles.
+//   warp 1      : TMEM allocation + single-thread tcgen05.mma issue (M=128, N=BN, K=16), two accumulator buffers in
+//                 TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
+//   warps 2..5  : epilogue — tcgen05.ld accumulator rows, transpose through padded shared memory so global
+//                 loads/stores are row-contiguous (128 B per 16 lanes), fused alpha/bias/FiLM/residual/activation,
+//                 fp16 (optionally hi+lo pair) and/or fp32 outputs, or raw fp32 split-K partials.
 //
 // Replaces cuDNN/cuBLAS calls behind nn.Conv2d / nn.Linear in the reference
 // (ldm/modules/diffusionmodules/openaimodel.py:204,230,241,519,685; ldm/modules/attention.py:40-60,161-168,233-248).
@@ -14,18 +18,29 @@
 #include "host.h"
 #include "ptx.cuh"
 
+#include <algorithm>
+
 namespace sdb {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_BYTES = BM * BK * 2;
+constexpr int MAX_SRC = 4;
+constexpr int STAGING_BYTES = 4 * 32 * 33 * 4;
+
+struct TmapPack {
+  CUtensorMap a[MAX_SRC];
+  CUtensorMap b;
+};
 
 struct GemmArgs {
   int M, N;
-  int taps, chunks0, chunks_tot;  // 64-channel chunks in source 0 / both sources
+  int taps, nsrc;
+  int cb[MAX_SRC + 1];  // cumulative 64-channel chunk boundaries of the A sources; cb[nsrc] = chunks per tap
   int H, W, NB;
   int TW, TH, TN, tiles_x, tiles_y;
-  int k_iters, iters_per_split;
+  int k_iters, iters_per_split, splits;
+  int m_tiles, n_tiles;
   float alpha;
   const float* bias;
   const float* film;
@@ -34,6 +49,7 @@ struct GemmArgs {
   const float* residual;
   int ldr;
   __half* out_f16;
+  __half* out_f16_lo;
   float* out_f32;
   int ldo;
   float* ws;
@@ -42,6 +58,11 @@ struct GemmArgs {
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == SDB_ACT_QUICK_GELU) return x * sigmoidf_(1.702f * x);
+  if (act == SDB_ACT_SILU) return x * sigmoidf_(x);
+  return x;
+}
 
 __device__ __forceinline__ bool map_row(const GemmArgs& p, int m_tile, int r, int& out_row) {
   if (p.taps == 1) {
@@ -60,89 +81,130 @@ __device__ __forceinline__ bool map_row(const GemmArgs& p, int m_tile, int r, in
   return gy < p.H && gn < p.NB;
 }
 
-// v[32] holds alpha-scaled-to-be accumulators for columns [col0, col0+32) of row `row`.
-__device__ __forceinline__ void epilogue_store(const GemmArgs& p, int row, int col0, int ncols, float (&v)[32]) {
-  int nvalid = min(32, ncols - col0);
-  if (nvalid <= 0) return;
-  const float* film = p.film ? p.film + static_cast<size_t>(row / p.rows_per_sample) * p.ldf : nullptr;
-  const float* res = p.residual ? p.residual + static_cast<size_t>(row) * p.ldr : nullptr;
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    if (j < nvalid) {
-      float x = v[j] * p.alpha;
-      if (p.bias) x += __ldg(p.bias + col0 + j);
-      if (film) x += __ldg(film + col0 + j);
-      if (res) x += res[col0 + j];
-      if (p.act == SDB_ACT_QUICK_GELU) x = x * sigmoidf_(1.702f * x);
-      else if (p.act == SDB_ACT_SILU) x = x * sigmoidf_(x);
-      v[j] = x;
-    }
+// One element of the fused epilogue (after alpha/bias which are column-only).
+__device__ __forceinline__ void store_elem(const GemmArgs& p, float x, int orow, int sample, int col, bool finish) {
+  if (finish) {
+    if (p.film) x += p.film[static_cast<size_t>(sample) * p.ldf + col];
+    if (p.residual) x += p.residual[static_cast<size_t>(orow) * p.ldr + col];
+    x = apply_act(x, p.act);
   }
-  size_t o = static_cast<size_t>(row) * p.ldo + col0;
-  bool vec = (nvalid == 32) && ((p.ldo & 7) == 0) && ((col0 & 7) == 0);
-  if (p.out_f32) {
-    float* d = p.out_f32 + o;
-    if (vec) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(d + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-    } else {
-      for (int j = 0; j < nvalid; ++j) d[j] = v[j];
-    }
-  }
+  size_t o = static_cast<size_t>(orow) * p.ldo + col;
+  if (p.out_f32) p.out_f32[o] = x;
   if (p.out_f16) {
-    __half* d = p.out_f16 + o;
-    if (vec) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        __half2 h0 = __floats2half2_rn(v[j], v[j + 1]);
-        __half2 h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
-        __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]);
-        __half2 h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
-        uint4 u;
-        u.x = *reinterpret_cast<uint32_t*>(&h0);
-        u.y = *reinterpret_cast<uint32_t*>(&h1);
-        u.z = *reinterpret_cast<uint32_t*>(&h2);
-        u.w = *reinterpret_cast<uint32_t*>(&h3);
-        *reinterpret_cast<uint4*>(d + j) = u;
+    __half h = __float2half_rn(x);
+    p.out_f16[o] = h;
+    if (p.out_f16_lo) p.out_f16_lo[o] = __float2half_rn(x - __half2float(h));
+  }
+}
+
+// Drain one 32x32 fp32 chunk that sits in the warp's padded staging tile (row = TMEM lane, col = chunk column) to
+// global memory with row-contiguous accesses: 16 lanes x 2 columns per row, two rows per instruction.
+//   mode 0: fused epilogue (alpha, bias, FiLM, residual, activation)   mode 1: raw split-K partial   mode 2: values
+//   already final (GEGLU computed in row layout)
+__device__ __forceinline__ void drain_chunk(const GemmArgs& p, const float* stage, int lane, int my_row, int my_sample,
+                                            bool my_valid, int ocol0, int ncols, int mode, int split) {
+  const int l16 = lane & 15, rsel = lane >> 4;
+  const int col = ocol0 + 2 * l16;
+  const bool c0 = col < ncols, c1 = col + 1 < ncols;
+  float b0 = 0.f, b1 = 0.f;
+  if (mode == 0 && p.bias) {
+    if (c0) b0 = __ldg(p.bias + col);
+    if (c1) b1 = __ldg(p.bias + col + 1);
+  }
+  const bool vec = c1 && ((p.ldo & 1) == 0) && (!p.residual || (p.ldr & 1) == 0) && (!p.film || (p.ldf & 1) == 0);
+#pragma unroll 4
+  for (int it = 0; it < 16; ++it) {
+    const int r = it * 2 + rsel;
+    const int orow = __shfl_sync(0xffffffffu, my_row, r);
+    const int sample = __shfl_sync(0xffffffffu, my_sample, r);
+    const bool valid = __shfl_sync(0xffffffffu, my_valid ? 1 : 0, r) != 0;
+    if (!valid || !c0) continue;
+    float x0 = stage[r * 33 + 2 * l16];
+    float x1 = stage[r * 33 + 2 * l16 + 1];
+    if (mode == 1) {
+      float* dst = p.ws + (static_cast<size_t>(split) * p.M + orow) * p.N + col;
+      if (c1 && (p.N & 1) == 0) {
+        *reinterpret_cast<float2*>(dst) = make_float2(x0, x1);
+      } else {
+        dst[0] = x0;
+        if (c1) dst[1] = x1;
       }
-    } else {
-      for (int j = 0; j < nvalid; ++j) d[j] = __float2half_rn(v[j]);
+      continue;
+    }
+    if (mode == 0) {
+      x0 = x0 * p.alpha + b0;
+      x1 = x1 * p.alpha + b1;
+    }
+    if (!vec) {
+      store_elem(p, x0, orow, sample, col, mode == 0);
+      if (c1) store_elem(p, x1, orow, sample, col + 1, mode == 0);
+      continue;
+    }
+    if (mode == 0) {
+      if (p.film) {
+        float2 f = *reinterpret_cast<const float2*>(p.film + static_cast<size_t>(sample) * p.ldf + col);
+        x0 += f.x;
+        x1 += f.y;
+      }
+      if (p.residual) {
+        float2 rv = *reinterpret_cast<const float2*>(p.residual + static_cast<size_t>(orow) * p.ldr + col);
+        x0 += rv.x;
+        x1 += rv.y;
+      }
+      x0 = apply_act(x0, p.act);
+      x1 = apply_act(x1, p.act);
+    }
+    const size_t o = static_cast<size_t>(orow) * p.ldo + col;
+    if (p.out_f32) *reinterpret_cast<float2*>(p.out_f32 + o) = make_float2(x0, x1);
+    if (p.out_f16) {
+      __half2 h = __floats2half2_rn(x0, x1);
+      *reinterpret_cast<__half2*>(p.out_f16 + o) = h;
+      if (p.out_f16_lo) {
+        float2 hf = __half22float2(h);
+        *reinterpret_cast<__half2*>(p.out_f16_lo + o) = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+      }
     }
   }
 }
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(192, 1)
-    gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                   const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
+template <int BN>
+struct GemmCfg {
+  static constexpr int STAGES = BN <= 32 ? 8 : BN <= 64 ? 8 : BN <= 128 ? 6 : BN <= 160 ? 5 : 4;
+  static constexpr int TMEM_COLS = BN <= 32 ? 64 : BN <= 64 ? 128 : BN <= 128 ? 256 : 512;  // two accumulators
+  static constexpr int SMEM = STAGES * (A_BYTES + BN * BK * 2) + STAGING_BYTES + 1024;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__ TmapPack tm, const GemmArgs p) {
+  constexpr int STAGES = GemmCfg<BN>::STAGES;
   constexpr int B_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  constexpr int TMEM_COLS = GemmCfg<BN>::TMEM_COLS;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* staging = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
   __shared__ uint64_t full_bar[STAGES];
   __shared__ uint64_t empty_bar[STAGES];
-  __shared__ uint64_t acc_bar;
+  __shared__ uint64_t acc_full[2];
+  __shared__ uint64_t acc_empty[2];
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m_tile = blockIdx.x;
-  const int n_tile = blockIdx.y;
-  const int split = blockIdx.z;
-  const int it_begin = split * p.iters_per_split;
-  const int it_end = min(p.k_iters, it_begin + p.iters_per_split);
+  const int tiles_total = p.m_tiles * p.n_tiles * p.splits;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA0);
-    tma_prefetch_desc(&tmA1);
-    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < p.nsrc; ++i) tma_prefetch_desc(&tm.a[i]);
+    tma_prefetch_desc(&tm.b);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(&acc_bar, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 4);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -156,95 +218,106 @@ __global__ void __launch_bounds__(192, 1)
 
   if (warp == 0) {
     if (elect_one()) {
-      int x0 = 0, y0 = 0, n0 = 0;
-      if (p.taps == 1) {
-        x0 = m_tile * BM;
-      } else {
-        int tx = m_tile % p.tiles_x;
-        int t2 = m_tile / p.tiles_x;
-        x0 = tx * p.TW;
-        y0 = (t2 % p.tiles_y) * p.TH;
-        n0 = (t2 / p.tiles_y) * p.TN;
-      }
-      for (int it = it_begin; it < it_end; ++it) {
-        int i = it - it_begin;
-        int s = i % STAGES;
-        uint32_t ph = (i / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
-        int tap = it / p.chunks_tot;
-        int cc = it - tap * p.chunks_tot;
-        int dx = 0, dy = 0;
-        if (p.taps == 9) {
-          dy = tap / 3 - 1;
-          dx = tap % 3 - 1;
+      uint32_t i = 0;  // ring position, continues across tiles
+      for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
+        const int m_tile = tile % p.m_tiles;
+        const int rest = tile / p.m_tiles;
+        const int n_tile = rest % p.n_tiles;
+        const int split = rest / p.n_tiles;
+        const int it_begin = split * p.iters_per_split;
+        const int it_end = min(p.k_iters, it_begin + p.iters_per_split);
+        int x0 = 0, y0 = 0, n0 = 0;
+        if (p.taps == 1) {
+          x0 = m_tile * BM;
+        } else {
+          int tx = m_tile % p.tiles_x;
+          int t2 = m_tile / p.tiles_x;
+          x0 = tx * p.TW;
+          y0 = (t2 % p.tiles_y) * p.TH;
+          n0 = (t2 / p.tiles_y) * p.TN;
         }
-        uint8_t* a_s = smem + s * STAGE_BYTES;
-        uint8_t* b_s = a_s + A_BYTES;
-        if (cc < p.chunks0)
-          tma_load_4d(a_s, &tmA0, &full_bar[s], cc * BK, x0 + dx, y0 + dy, n0);
-        else
-          tma_load_4d(a_s, &tmA1, &full_bar[s], (cc - p.chunks0) * BK, x0 + dx, y0 + dy, n0);
-        tma_load_2d(b_s, &tmB, &full_bar[s], it * BK, n_tile * BN);
+        const int cpt = p.cb[p.nsrc];
+        for (int it = it_begin; it < it_end; ++it, ++i) {
+          const int s = i % STAGES;
+          const uint32_t ph = (i / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+          const int tap = it / cpt;
+          const int cc = it - tap * cpt;
+          int dx = 0, dy = 0;
+          if (p.taps == 9) {
+            dy = tap / 3 - 1;
+            dx = tap % 3 - 1;
+          }
+          int src = 0;
+          while (src + 1 < p.nsrc && cc >= p.cb[src + 1]) ++src;
+          uint8_t* a_s = smem + s * STAGE_BYTES;
+          tma_load_4d(a_s, &tm.a[src], &full_bar[s], (cc - p.cb[src]) * BK, x0 + dx, y0 + dy, n0);
+          tma_load_2d(a_s + A_BYTES, &tm.b, &full_bar[s], it * BK, n_tile * BN);
+        }
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
-      for (int it = it_begin; it < it_end; ++it) {
-        int i = it - it_begin;
-        int s = i % STAGES;
-        uint32_t ph = (i / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t i = 0, local = 0;
+      for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x, ++local) {
+        const int split = (tile / p.m_tiles) / p.n_tiles;
+        const int it_begin = split * p.iters_per_split;
+        const int it_end = min(p.k_iters, it_begin + p.iters_per_split);
+        const uint32_t ab = local & 1;
+        mbar_wait(&acc_empty[ab], ((local >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
-        uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
-        uint64_t da = umma_desc_k128(a_addr);
-        uint64_t db = umma_desc_k128(a_addr + A_BYTES);
+        const uint32_t d_addr = tmem_d + ab * BN;
+        for (int it = it_begin; it < it_end; ++it, ++i) {
+          const int s = i % STAGES;
+          const uint32_t ph = (i / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+          const uint64_t da = umma_desc_k128(a_addr);
+          const uint64_t db = umma_desc_k128(a_addr + A_BYTES);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // advance 32 bytes (16 fp16) along K inside the 128-byte swizzle atom: +2 in the (addr>>4) field
-          umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 32 bytes (16 fp16) along K inside the 128-byte swizzle atom: +2 in the (addr>>4) field
+            umma_f16(d_addr, da + 2 * k, db + 2 * k, idesc, (it > it_begin || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
         }
-        umma_commit(&empty_bar[s]);
+        umma_commit(&acc_full[ab]);
       }
-      umma_commit(&acc_bar);
     }
   } else {
     // epilogue warps 2..5 : TMEM lane group = warp % 4
     const int lg = warp & 3;
-    const int r = lg * 32 + lane;
-    int out_row;
-    bool valid = map_row(p, m_tile, r, out_row);
-    if (it_end > it_begin) {
-      mbar_wait(&acc_bar, 0);
+    float* stage = staging + lg * (32 * 33);
+    uint32_t local = 0;
+    for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x, ++local) {
+      const int m_tile = tile % p.m_tiles;
+      const int rest = tile / p.m_tiles;
+      const int n_tile = rest % p.n_tiles;
+      const int split = rest / p.n_tiles;
+      const uint32_t ab = local & 1;
+      int my_row;
+      const bool my_valid = map_row(p, m_tile, lg * 32 + lane, my_row);
+      const int my_sample = my_valid ? my_row / p.rows_per_sample : 0;
+      mbar_wait(&acc_full[ab], (local >> 1) & 1);
       tc_fence_after();
-    }
-    const uint32_t taddr = tmem_d + (static_cast<uint32_t>(lg * 32) << 16);
-    if (p.ws) {
-      // split-K: raw fp32 partial tile
-      float* dst = p.ws + (static_cast<size_t>(split) * p.M + out_row) * p.N + n_tile * BN;
+      const uint32_t taddr = tmem_d + ab * BN + (static_cast<uint32_t>(lg * 32) << 16);
+      if (p.act == SDB_ACT_GEGLU && !p.ws) {
+        constexpr int HALF = BN / 2;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t rr[32];
-        tmem_ld32(taddr + c * 32, rr);
-        tmem_ld_wait();
-        if (valid) {
-          int col0 = n_tile * BN + c * 32;
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.N) dst[c * 32 + j] = (it_end > it_begin) ? __uint_as_float(rr[j]) : 0.f;
-        }
-      }
-    } else if (p.act == SDB_ACT_GEGLU) {
-      constexpr int HALF = BN / 2;
-#pragma unroll 1
-      for (int c = 0; c < HALF / 32; ++c) {
-        uint32_t xr[32], gr[32];
-        tmem_ld32(taddr + c * 32, xr);
-        tmem_ld32(taddr + HALF + c * 32, gr);
-        tmem_ld_wait();
-        if (valid) {
-          float v[32];
-          int colx = n_tile * BN + c * 32;  // accumulator column of x; gate at +HALF
+        for (int c = 0; c < HALF / 32; ++c) {
+          uint32_t xr[32], gr[32];
+          tmem_ld32(taddr + c * 32, xr);
+          tmem_ld32(taddr + HALF + c * 32, gr);
+          tmem_ld_wait();
+          if (c == HALF / 32 - 1) {  // accumulator fully read: hand the buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[ab]);
+          }
+          const int colx = n_tile * BN + c * 32;  // accumulator column of the value half; gate at +HALF
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             float x = __uint_as_float(xr[j]) * p.alpha;
@@ -253,33 +326,28 @@ __global__ void __launch_bounds__(192, 1)
               x += __ldg(p.bias + colx + j);
               g += __ldg(p.bias + colx + HALF + j);
             }
-            v[j] = x * gelu_erf(g);
+            stage[lane * 33 + j] = x * gelu_erf(g);
           }
-          int ocol = n_tile * HALF + c * 32;
-          size_t o = static_cast<size_t>(out_row) * p.ldo + ocol;
-          if (p.out_f16) {
-            __half* d = p.out_f16 + o;
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) *reinterpret_cast<__half2*>(d + j) = __floats2half2_rn(v[j], v[j + 1]);
-          }
-          if (p.out_f32) {
-            float* d = p.out_f32 + o;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) d[j] = v[j];
-          }
+          __syncwarp();
+          drain_chunk(p, stage, lane, my_row, my_sample, my_valid, n_tile * HALF + c * 32, p.N / 2, 2, split);
+          __syncwarp();
         }
-      }
-    } else {
+      } else {
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t rr[32];
-        tmem_ld32(taddr + c * 32, rr);
-        tmem_ld_wait();
-        if (valid) {
-          float v[32];
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t rr[32];
+          tmem_ld32(taddr + c * 32, rr);
+          tmem_ld_wait();
+          if (c == BN / 32 - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[ab]);
+          }
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
-          epilogue_store(p, out_row, n_tile * BN + c * 32, p.N, v);
+          for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(rr[j]);
+          __syncwarp();
+          drain_chunk(p, stage, lane, my_row, my_sample, my_valid, n_tile * BN + c * 32, p.N, p.ws ? 1 : 0, split);
+          __syncwarp();
         }
       }
     }
@@ -292,44 +360,52 @@ __global__ void __launch_bounds__(192, 1)
   }
 }
 
-// split-K second pass: sum partials and apply the fused epilogue
-__global__ void splitk_epilogue_kernel(const GemmArgs p, int splits) {
-  size_t total = static_cast<size_t>(p.M) * p.N;
-  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    int row = static_cast<int>(idx / p.N);
-    int col = static_cast<int>(idx - static_cast<size_t>(row) * p.N);
-    float acc = 0.f;
-    for (int s = 0; s < splits; ++s) acc += p.ws[static_cast<size_t>(s) * total + idx];
-    float x = acc * p.alpha;
-    if (p.bias) x += p.bias[col];
-    if (p.film) x += p.film[static_cast<size_t>(row / p.rows_per_sample) * p.ldf + col];
-    if (p.residual) x += p.residual[static_cast<size_t>(row) * p.ldr + col];
-    if (p.act == SDB_ACT_QUICK_GELU) x = x * sigmoidf_(1.702f * x);
-    else if (p.act == SDB_ACT_SILU) x = x * sigmoidf_(x);
-    size_t o = static_cast<size_t>(row) * p.ldo + col;
-    if (p.out_f32) p.out_f32[o] = x;
-    if (p.out_f16) p.out_f16[o] = __float2half_rn(x);
+// split-K second pass: sum partials and apply the fused epilogue (4 columns per thread when N % 4 == 0)
+template <int VEC>
+__global__ void __launch_bounds__(256) splitk_epilogue_kernel(const GemmArgs p, int splits) {
+  const size_t total = static_cast<size_t>(p.M) * p.N;
+  const size_t nvec = total / VEC;
+  for (size_t v = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; v < nvec;
+       v += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t idx = v * VEC;
+    const int row = static_cast<int>(idx / p.N);
+    const int col = static_cast<int>(idx - static_cast<size_t>(row) * p.N);
+    float acc[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+    for (int s = 0; s < splits; ++s) {
+      const float* src = p.ws + static_cast<size_t>(s) * total + idx;
+      if (VEC == 4) {
+        float4 t = *reinterpret_cast<const float4*>(src);
+        acc[0] += t.x;
+        acc[1] += t.y;
+        acc[2] += t.z;
+        acc[3] += t.w;
+      } else {
+        acc[0] += src[0];
+      }
+    }
+    const int sample = row / p.rows_per_sample;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      float x = acc[j] * p.alpha + (p.bias ? p.bias[col + j] : 0.f);
+      store_elem(p, x, row, sample, col + j, true);
+    }
   }
 }
 
 template <int BN>
-struct GemmCfg {
-  static constexpr int STAGES = BN <= 64 ? 4 : BN <= 128 ? 3 : 4;  // <=128: 2 CTAs/SM co-reside (97 KB each)
-  static constexpr int SMEM = STAGES * (A_BYTES + BN * BK * 2) + 1024;
-};
-
-template <int BN>
-static int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const GemmArgs& p,
-                       dim3 grid, cudaStream_t st) {
+static int launch_gemm(const TmapPack& tm, const GemmArgs& p, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
-  auto kern = gemm_tc_kernel<BN, Cfg::STAGES>;
+  auto kern = gemm_tc_kernel<BN>;
   static bool configured = false;
   if (!configured) {
     SDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     configured = true;
   }
-  kern<<<grid, 192, Cfg::SMEM, st>>>(a0, a1, b, p);
+  const int tiles = p.m_tiles * p.n_tiles * p.splits;
+  const int grid = std::min(tiles, sm_count());
+  kern<<<grid, 192, Cfg::SMEM, st>>>(tm, p);
   SDB_LAUNCH_CHECK();
   return 0;
 }
@@ -340,16 +416,20 @@ static int pow2_divisor(int v, int cap) {
   return p;
 }
 
-// Tile model used to pick (block_n, split-K): every 64-wide K step of a 128 x bn tile moves (128 + bn) * 128 B
-// from L2 (the binding resource for 1-CTA tiles), the epilogue drains bn columns, plus a fixed launch/prologue cost;
-// CTAs run in waves of sm_count. Split-K adds an fp32 partial round trip and a second kernel.
+// Tile model used to pick (block_n, split-K). Per CTA the 64-wide K step of a 128 x bn tile moves (128 + bn) * 128 B
+// from L2 (the binding resource for 1-CTA tiles); the epilogue drains bn columns and, in the persistent kernel,
+// overlaps the next tile's main loop, so a tile costs max(mainloop, epilogue) plus a fixed hand-off. CTAs run in
+// waves of sm_count. Split-K adds an fp32 partial round trip and a second kernel.
 static double tile_cost(int n, long m_tiles, int k_iters, int bn, int splits, long M) {
   long nt = (n + bn - 1) / bn;
   long tiles = m_tiles * nt * splits;
   long waves = (tiles + sm_count() - 1) / sm_count();
-  double per_tile = static_cast<double>((k_iters + splits - 1) / splits) * (128.0 + bn) + 2.0 * bn + 300.0;
-  double t = waves * per_tile;
-  if (splits > 1) t += 1500.0 + static_cast<double>(splits) * M * n / (sm_count() * 64.0);
+  double mainloop = static_cast<double>((k_iters + splits - 1) / splits) * (128.0 + bn) * 1.6;
+  double epi = 10.0 * bn + 200.0;
+  double first = mainloop + epi;                       // first tile of a CTA cannot overlap
+  double steady = std::max(mainloop, epi) + 150.0;
+  double t = first + (waves - 1) * steady + 800.0;
+  if (splits > 1) t += 2500.0 + 6.0 * static_cast<double>(splits) * M * n / (sm_count() * 256.0);
   return t;
 }
 
@@ -391,11 +471,21 @@ extern "C" int sdb_gemm(const sdb_gemm_desc* d, sdb_stream_t stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SDB_CHECK(d && d->a0 && d->b, "sdb_gemm: null operand");
   SDB_CHECK(d->taps == 1 || d->taps == 9, "sdb_gemm: taps must be 1 or 9 (got %d)", d->taps);
-  SDB_CHECK(d->c0 > 0 && d->c0 % 64 == 0 && d->c1 >= 0 && d->c1 % 64 == 0,
-            "sdb_gemm: channel counts must be multiples of 64 (c0=%d c1=%d)", d->c0, d->c1);
-  SDB_CHECK((d->c1 == 0) == (d->a1 == nullptr), "sdb_gemm: a1/c1 mismatch");
+  const void* srcs[MAX_SRC] = {d->a0, d->a1, d->a2, d->a3};
+  const int chans[MAX_SRC] = {d->c0, d->c1, d->c2, d->c3};
+  int nsrc = 0, ctot = 0;
+  for (int i = 0; i < MAX_SRC; ++i) {
+    if (srcs[i] == nullptr) break;
+    SDB_CHECK(chans[i] > 0 && chans[i] % 64 == 0, "sdb_gemm: channel count of source %d must be a positive multiple of 64 (got %d)",
+              i, chans[i]);
+    ++nsrc;
+    ctot += chans[i];
+  }
+  for (int i = nsrc; i < MAX_SRC; ++i)
+    SDB_CHECK(srcs[i] == nullptr && chans[i] == 0, "sdb_gemm: A sources must be contiguous (a%d/c%d)", i, i);
   SDB_CHECK(d->nb > 0 && d->h > 0 && d->w > 0 && d->n > 0, "sdb_gemm: bad dims");
   SDB_CHECK(d->out_f16 || d->out_f32, "sdb_gemm: no output");
+  SDB_CHECK(!d->out_f16_lo || d->out_f16, "sdb_gemm: out_f16_lo needs out_f16");
 
   GemmArgs p{};
   const long M = static_cast<long>(d->nb) * d->h * d->w;
@@ -403,9 +493,11 @@ extern "C" int sdb_gemm(const sdb_gemm_desc* d, sdb_stream_t stream) {
   p.M = static_cast<int>(M);
   p.N = d->n;
   p.taps = d->taps;
-  p.chunks0 = d->c0 / 64;
-  p.chunks_tot = (d->c0 + d->c1) / 64;
-  p.k_iters = d->taps * p.chunks_tot;
+  p.nsrc = nsrc;
+  p.cb[0] = 0;
+  for (int i = 0; i < nsrc; ++i) p.cb[i + 1] = p.cb[i] + chans[i] / 64;
+  for (int i = nsrc; i < MAX_SRC; ++i) p.cb[i + 1] = p.cb[nsrc];
+  p.k_iters = d->taps * p.cb[nsrc];
   p.H = d->h;
   p.W = d->w;
   p.NB = d->nb;
@@ -417,6 +509,7 @@ extern "C" int sdb_gemm(const sdb_gemm_desc* d, sdb_stream_t stream) {
   p.residual = d->residual;
   p.ldr = d->ldr > 0 ? d->ldr : d->n;
   p.out_f16 = static_cast<__half*>(d->out_f16);
+  p.out_f16_lo = static_cast<__half*>(d->out_f16_lo);
   p.out_f32 = d->out_f32;
   p.act = d->act;
   const bool geglu = d->act == SDB_ACT_GEGLU;
@@ -461,54 +554,57 @@ extern "C" int sdb_gemm(const sdb_gemm_desc* d, sdb_stream_t stream) {
               "sdb_gemm: split-K workspace too small");
     p.ws = d->workspace;
   }
+  p.splits = splits;
+  p.m_tiles = static_cast<int>(m_tiles);
+  p.n_tiles = (d->n + bn - 1) / bn;
+  SDB_CHECK(m_tiles * p.n_tiles * splits < (1L << 30), "sdb_gemm: too many tiles");
 
   // tensor maps
-  CUtensorMap tA0, tA1, tB;
-  const int ctot = d->c0 + d->c1;
-  auto make_a = [&](CUtensorMap* tm, const void* base, int c) -> int {
+  TmapPack tm;
+  for (int i = 0; i < nsrc; ++i) {
+    const int c = chans[i];
     if (d->taps == 1) {
       uint64_t dims[4] = {static_cast<uint64_t>(c), static_cast<uint64_t>(M), 1, 1};
       uint64_t str[3] = {static_cast<uint64_t>(c) * 2, static_cast<uint64_t>(c) * 2 * M,
                          static_cast<uint64_t>(c) * 2 * M};
       uint32_t box[4] = {64, 128, 1, 1};
-      return make_tmap_f16(tm, base, 4, dims, str, box);
+      if (make_tmap_f16(&tm.a[i], srcs[i], 4, dims, str, box)) return 1;
+    } else {
+      uint64_t dims[4] = {static_cast<uint64_t>(c), static_cast<uint64_t>(d->w), static_cast<uint64_t>(d->h),
+                          static_cast<uint64_t>(d->nb)};
+      uint64_t str[3] = {static_cast<uint64_t>(c) * 2, static_cast<uint64_t>(c) * 2 * d->w,
+                         static_cast<uint64_t>(c) * 2 * d->w * d->h};
+      uint32_t box[4] = {64, static_cast<uint32_t>(p.TW), static_cast<uint32_t>(p.TH), static_cast<uint32_t>(p.TN)};
+      if (make_tmap_f16(&tm.a[i], srcs[i], 4, dims, str, box)) return 1;
     }
-    uint64_t dims[4] = {static_cast<uint64_t>(c), static_cast<uint64_t>(d->w), static_cast<uint64_t>(d->h),
-                        static_cast<uint64_t>(d->nb)};
-    uint64_t str[3] = {static_cast<uint64_t>(c) * 2, static_cast<uint64_t>(c) * 2 * d->w,
-                       static_cast<uint64_t>(c) * 2 * d->w * d->h};
-    uint32_t box[4] = {64, static_cast<uint32_t>(p.TW), static_cast<uint32_t>(p.TH), static_cast<uint32_t>(p.TN)};
-    return make_tmap_f16(tm, base, 4, dims, str, box);
-  };
-  if (make_a(&tA0, d->a0, d->c0)) return 1;
-  if (d->a1) {
-    if (make_a(&tA1, d->a1, d->c1)) return 1;
-  } else {
-    tA1 = tA0;
   }
+  for (int i = nsrc; i < MAX_SRC; ++i) tm.a[i] = tm.a[0];
   {
     uint64_t K = static_cast<uint64_t>(d->taps) * ctot;
     uint64_t dims[2] = {K, static_cast<uint64_t>(d->n)};
     uint64_t str[1] = {K * 2};
     uint32_t box[2] = {64, static_cast<uint32_t>(bn)};
-    if (make_tmap_f16(&tB, d->b, 2, dims, str, box)) return 1;
+    if (make_tmap_f16(&tm.b, d->b, 2, dims, str, box)) return 1;
   }
 
-  dim3 grid(static_cast<unsigned>(m_tiles), static_cast<unsigned>((d->n + bn - 1) / bn), static_cast<unsigned>(splits));
   int rc;
   switch (bn) {
-    case 32: rc = launch_gemm<32>(tA0, tA1, tB, p, grid, st); break;
-    case 64: rc = launch_gemm<64>(tA0, tA1, tB, p, grid, st); break;
-    case 128: rc = launch_gemm<128>(tA0, tA1, tB, p, grid, st); break;
-    case 160: rc = launch_gemm<160>(tA0, tA1, tB, p, grid, st); break;
-    case 256: rc = launch_gemm<256>(tA0, tA1, tB, p, grid, st); break;
-    default: SDB_CHECK(false, "sdb_gemm: unsupported block_n %d", bn);
+    case 32: rc = launch_gemm<32>(tm, p, st); break;
+    case 64: rc = launch_gemm<64>(tm, p, st); break;
+    case 128: rc = launch_gemm<128>(tm, p, st); break;
+    case 160: rc = launch_gemm<160>(tm, p, st); break;
+    default: rc = launch_gemm<256>(tm, p, st); break;
   }
   if (rc) return rc;
   if (splits > 1) {
     size_t total = static_cast<size_t>(p.M) * p.N;
-    int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(sm_count()) * 8));
-    splitk_epilogue_kernel<<<blocks, 256, 0, st>>>(p, splits);
+    if (p.N % 4 == 0 && (p.ldo % 2 == 0)) {
+      int blocks = static_cast<int>(std::min<size_t>((total / 4 + 255) / 256, static_cast<size_t>(sm_count()) * 8));
+      splitk_epilogue_kernel<4><<<blocks, 256, 0, st>>>(p, splits);
+    } else {
+      int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(sm_count()) * 8));
+      splitk_epilogue_kernel<1><<<blocks, 256, 0, st>>>(p, splits);
+    }
     SDB_LAUNCH_CHECK();
   }
   return 0;

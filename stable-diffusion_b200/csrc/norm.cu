@@ -11,27 +11,34 @@ namespace sdb {
 constexpr int GN_THREADS = 256;
 constexpr int GN_MAX_CPT = 12;  // channels per thread: C <= 3072
 
-// pass 1: per (sample, group) sum / sum of squares.  grid = (slabs, nb)
+// pass 1: per (sample, group) sum / sum of squares.  grid = (slabs, nb). Thread t owns channel (t % cw) [+ k*cw] of
+// rows (t / cw) + k * (256 / cw): consecutive threads read consecutive channels (coalesced); per-channel partials are
+// combined in shared memory, reduced per group by one warp each, and added to the fp64 global accumulators.
 __global__ void __launch_bounds__(GN_THREADS)
     gn_stats_kernel(const float* __restrict__ x0, const float* __restrict__ x1, int c0, int c1, int hw, int groups,
-                    int rows_per_block, double* __restrict__ stats) {
+                    int rows_per_block, int cw, double* __restrict__ stats) {
+  extern __shared__ float gn_smem[];  // [2][C]
   const int C = c0 + c1;
   const int cpg = C / groups;
   const int n = blockIdx.y;
   const int r0 = blockIdx.x * rows_per_block;
   const int r1 = min(hw, r0 + rows_per_block);
-  __shared__ double gs[64][2];
-  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) (&gs[0][0])[i] = 0.0;
+  float* sum_s = gn_smem;
+  float* sum_q = gn_smem + C;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) gn_smem[i] = 0.f;
   __syncthreads();
+  const int tc = threadIdx.x % cw;
+  const int tr = threadIdx.x / cw;
+  const int rstep = GN_THREADS / cw;
   float s[GN_MAX_CPT], q[GN_MAX_CPT];
 #pragma unroll
   for (int j = 0; j < GN_MAX_CPT; ++j) s[j] = q[j] = 0.f;
-  for (int r = r0; r < r1; ++r) {
+  for (int r = r0 + tr; r < r1; r += rstep) {
     const float* p0 = x0 + (static_cast<size_t>(n) * hw + r) * c0;
     const float* p1 = x1 ? x1 + (static_cast<size_t>(n) * hw + r) * c1 : nullptr;
 #pragma unroll
     for (int j = 0; j < GN_MAX_CPT; ++j) {
-      int c = threadIdx.x + j * GN_THREADS;
+      int c = tc + j * cw;
       if (c < C) {
         float v = c < c0 ? p0[c] : p1[c - c0];
         s[j] += v;
@@ -41,16 +48,35 @@ __global__ void __launch_bounds__(GN_THREADS)
   }
 #pragma unroll
   for (int j = 0; j < GN_MAX_CPT; ++j) {
-    int c = threadIdx.x + j * GN_THREADS;
+    int c = tc + j * cw;
     if (c < C) {
-      int g = c / cpg;
-      atomicAdd(&gs[g][0], static_cast<double>(s[j]));
-      atomicAdd(&gs[g][1], static_cast<double>(q[j]));
+      if (rstep == 1) {
+        sum_s[c] = s[j];
+        sum_q[c] = q[j];
+      } else {
+        atomicAdd(&sum_s[c], s[j]);
+        atomicAdd(&sum_q[c], q[j]);
+      }
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x)
-    atomicAdd(&stats[static_cast<size_t>(n) * groups * 2 + i], (&gs[0][0])[i]);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int g = warp; g < groups; g += GN_THREADS / 32) {
+    float a = 0.f, b = 0.f;
+    for (int c = lane; c < cpg; c += 32) {
+      a += sum_s[g * cpg + c];
+      b += sum_q[g * cpg + c];
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) {
+      atomicAdd(&stats[(static_cast<size_t>(n) * groups + g) * 2], static_cast<double>(a));
+      atomicAdd(&stats[(static_cast<size_t>(n) * groups + g) * 2 + 1], static_cast<double>(b));
+    }
+  }
 }
 
 // pass 2: normalise (+SiLU) -> fp16, optional raw fp16 cast. grid = (slabs, nb)
@@ -58,7 +84,7 @@ __global__ void __launch_bounds__(GN_THREADS)
     gn_apply_kernel(const float* __restrict__ x0, const float* __restrict__ x1, int c0, int c1, int hw, int groups,
                     int rows_per_block, const double* __restrict__ stats, const float* __restrict__ gamma,
                     const float* __restrict__ beta, float eps, int silu, __half* __restrict__ out,
-                    __half* __restrict__ raw) {
+                    __half* __restrict__ raw, __half* __restrict__ out_lo, __half* __restrict__ raw_lo) {
   const int C = c0 + c1;
   const int cpg = C / groups;
   const int n = blockIdx.y;
@@ -96,12 +122,28 @@ __global__ void __launch_bounds__(GN_THREADS)
     u.x = *reinterpret_cast<uint32_t*>(&h0);
     u.y = *reinterpret_cast<uint32_t*>(&h1);
     *reinterpret_cast<uint2*>(out + row * C + c) = u;
+    if (out_lo) {  // low halves of the hi/lo operand split: fp16(y - float(fp16(y)))
+      float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+      __half2 l0 = __floats2half2_rn(o[0] - f0.x, o[1] - f0.y), l1 = __floats2half2_rn(o[2] - f1.x, o[3] - f1.y);
+      uint2 w;
+      w.x = *reinterpret_cast<uint32_t*>(&l0);
+      w.y = *reinterpret_cast<uint32_t*>(&l1);
+      *reinterpret_cast<uint2*>(out_lo + row * C + c) = w;
+    }
     if (raw) {
       __half2 r0h = __floats2half2_rn(in[0], in[1]), r1h = __floats2half2_rn(in[2], in[3]);
       uint2 w;
       w.x = *reinterpret_cast<uint32_t*>(&r0h);
       w.y = *reinterpret_cast<uint32_t*>(&r1h);
       *reinterpret_cast<uint2*>(raw + row * C + c) = w;
+      if (raw_lo) {
+        float2 f0 = __half22float2(r0h), f1 = __half22float2(r1h);
+        __half2 l0 = __floats2half2_rn(in[0] - f0.x, in[1] - f0.y), l1 = __floats2half2_rn(in[2] - f1.x, in[3] - f1.y);
+        uint2 w2;
+        w2.x = *reinterpret_cast<uint32_t*>(&l0);
+        w2.y = *reinterpret_cast<uint32_t*>(&l1);
+        *reinterpret_cast<uint2*>(raw_lo + row * C + c) = w2;
+      }
     }
   }
 }
@@ -178,7 +220,8 @@ using namespace sdb;
 
 extern "C" int sdb_groupnorm(const float* x0, const float* x1, int32_t c0, int32_t c1, int32_t nb, int32_t hw,
                              int32_t groups, const float* gamma, const float* beta, float eps, int32_t silu,
-                             void* out_f16, void* raw_f16, void* stats_ws, sdb_stream_t stream) {
+                             void* out_f16, void* raw_f16, void* out_lo_f16, void* raw_lo_f16, void* stats_ws,
+                             sdb_stream_t stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int C = c0 + c1;
   SDB_CHECK(x0 && out_f16 && stats_ws && gamma && beta, "sdb_groupnorm: null pointer");
@@ -188,18 +231,29 @@ extern "C" int sdb_groupnorm(const float* x0, const float* x1, int32_t c0, int32
   SDB_CHECK(C <= GN_THREADS * GN_MAX_CPT, "sdb_groupnorm: C=%d too large", C);
   size_t stats_bytes = static_cast<size_t>(nb) * groups * 2 * sizeof(double);
   SDB_CUDA(cudaMemsetAsync(stats_ws, 0, stats_bytes, st));
-  // enough blocks to fill the machine, >= 8 rows per block
+  SDB_CHECK(!raw_lo_f16 || raw_f16, "sdb_groupnorm: raw_lo needs raw");
+  // channel-lane width: threads of a block cover cw channels x (256 / cw) rows at a time
+  int cw = GN_THREADS;
+  while (cw > 32 && cw / 2 >= C) cw /= 2;
+  const int rstep = GN_THREADS / cw;
+  // enough blocks to fill the machine (a few waves), at least `rstep` rows per block
   int target_blocks = sm_count() * 4;
-  int slabs = std::max(1, std::min((hw + 7) / 8, (target_blocks + nb - 1) / nb));
+  int slabs = std::max(1, std::min((hw + rstep - 1) / rstep, (target_blocks + nb - 1) / nb));
   int rows_per_block = (hw + slabs - 1) / slabs;
   slabs = (hw + rows_per_block - 1) / rows_per_block;
   dim3 grid(slabs, nb);
-  gn_stats_kernel<<<grid, GN_THREADS, 0, st>>>(x0, x1, c0, c1, hw, groups, rows_per_block,
-                                               static_cast<double*>(stats_ws));
+  gn_stats_kernel<<<grid, GN_THREADS, 2 * C * sizeof(float), st>>>(x0, x1, c0, c1, hw, groups, rows_per_block, cw,
+                                                                    static_cast<double*>(stats_ws));
   SDB_LAUNCH_CHECK();
-  gn_apply_kernel<<<grid, GN_THREADS, 0, st>>>(x0, x1, c0, c1, hw, groups, rows_per_block,
-                                               static_cast<const double*>(stats_ws), gamma, beta, eps, silu,
-                                               static_cast<__half*>(out_f16), static_cast<__half*>(raw_f16));
+  // apply: ~8 rows per block or more
+  int aslabs = std::max(1, std::min((hw + 7) / 8, (target_blocks + nb - 1) / nb));
+  int arows = (hw + aslabs - 1) / aslabs;
+  aslabs = (hw + arows - 1) / arows;
+  dim3 agrid(aslabs, nb);
+  gn_apply_kernel<<<agrid, GN_THREADS, 0, st>>>(x0, x1, c0, c1, hw, groups, arows,
+                                                static_cast<const double*>(stats_ws), gamma, beta, eps, silu,
+                                                static_cast<__half*>(out_f16), static_cast<__half*>(raw_f16),
+                                                static_cast<__half*>(out_lo_f16), static_cast<__half*>(raw_lo_f16));
   SDB_LAUNCH_CHECK();
   return 0;
 }

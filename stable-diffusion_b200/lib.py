@@ -15,8 +15,8 @@ ACT_NONE, ACT_GEGLU, ACT_QUICK_GELU, ACT_SILU = 0, 1, 2, 3
 
 class GemmDesc(C.Structure):
     _fields_ = [
-        ("a0", C.c_void_p), ("a1", C.c_void_p),
-        ("c0", C.c_int32), ("c1", C.c_int32),
+        ("a0", C.c_void_p), ("a1", C.c_void_p), ("a2", C.c_void_p), ("a3", C.c_void_p),
+        ("c0", C.c_int32), ("c1", C.c_int32), ("c2", C.c_int32), ("c3", C.c_int32),
         ("nb", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
         ("taps", C.c_int32),
         ("b", C.c_void_p),
@@ -30,6 +30,7 @@ class GemmDesc(C.Structure):
         ("ldr", C.c_int32),
         ("act", C.c_int32),
         ("out_f16", C.c_void_p),
+        ("out_f16_lo", C.c_void_p),
         ("out_f32", C.c_void_p),
         ("ldo", C.c_int32),
         ("block_n", C.c_int32),
@@ -61,7 +62,7 @@ SIGNATURES = {
     "sdb_launch_count": ([], C.c_longlong),
     "sdb_gemm": ([C.POINTER(GemmDesc), _P], C.c_int),
     "sdb_attention": ([C.POINTER(AttnDesc), _P], C.c_int),
-    "sdb_groupnorm": ([_P, _P, _I, _I, _I, _I, _I, _P, _P, _F, _I, _P, _P, _P, _P], C.c_int),
+    "sdb_groupnorm": ([_P, _P, _I, _I, _I, _I, _I, _P, _P, _F, _I, _P, _P, _P, _P, _P, _P], C.c_int),
     "sdb_layernorm": ([_P, _I, _I, _P, _P, _F, _P, _P, _P], C.c_int),
     "sdb_softmax_rows": ([_P, _I, _I, _F, _P, _P], C.c_int),
     "sdb_nchw_to_nhwc": ([_P, _I, _I, _I, _P, _P, _P], C.c_int),

@@ -50,23 +50,26 @@ def _chk32(t, name):
     assert t.dtype == torch.float32 and t.is_cuda and t.is_contiguous(), f"{name}: need contiguous cuda fp32"
 
 
-def gemm(a0, b, *, a1=None, nb=None, h=None, w=None, taps=1, bias=None, film=None, rows_per_sample=0,
-         residual=None, act=ACT_NONE, alpha=1.0, out_f16=None, out_f32=None, want_f16=False, want_f32=False,
-         n=None, block_n=0, splits=0, workspace=None):
+def gemm(a0, b, *, a1=None, a2=None, a3=None, nb=None, h=None, w=None, taps=1, bias=None, film=None,
+         rows_per_sample=0, residual=None, act=ACT_NONE, alpha=1.0, out_f16=None, out_f32=None, out_f16_lo=None,
+         want_f16=False, want_f32=False, want_lo=False, n=None, block_n=0, splits=0, workspace=None):
     """acc = A @ B^T with fused epilogue (see sdb_gemm in include/sdb200.h).
 
-    a0 (, a1): fp16 [..., c0] (, [..., c1]) NHWC activations or plain [rows, c] matrices.
-    b: fp16 [n, taps*(c0+c1)].
-    Returns (out_f16, out_f32) — whichever were requested / passed.
+    a0 (, a1, a2, a3): fp16 [..., c_i] NHWC activations or plain [rows, c_i] matrices, concatenated along K.
+    b: fp16 [n, taps*sum(c_i)].
+    Returns (out_f16, out_f32), or (out_f16, out_f32, out_f16_lo) when the hi/lo pair is requested.
     """
     _chk16(a0, "a0")
     _chk16(b, "b")
-    c0 = a0.shape[-1]
-    c1 = 0
-    if a1 is not None:
-        _chk16(a1, "a1")
-        c1 = a1.shape[-1]
-        assert a1.shape[:-1] == a0.shape[:-1]
+    srcs = [a0]
+    for t_ in (a1, a2, a3):
+        if t_ is None:
+            break
+        _chk16(t_, "a_i")
+        assert t_.shape[:-1] == a0.shape[:-1]
+        srcs.append(t_)
+    chans = [t_.shape[-1] for t_ in srcs]
+    c0 = chans[0]
     if taps == 9:
         assert a0.dim() == 4, "3x3 conv needs NHWC input"
         nb, h, w = a0.shape[0], a0.shape[1], a0.shape[2]
@@ -74,16 +77,21 @@ def gemm(a0, b, *, a1=None, nb=None, h=None, w=None, taps=1, bias=None, film=Non
         rows = a0.numel() // c0
         nb, h, w = 1, 1, rows
     n = b.shape[0] if n is None else n
-    assert b.shape[1] == taps * (c0 + c1), (b.shape, taps, c0, c1)
+    assert b.shape[1] == taps * sum(chans), (b.shape, taps, chans)
     M = nb * h * w
     n_out = n // 2 if act == ACT_GEGLU else n
-    if out_f16 is None and want_f16:
+    if out_f16 is None and (want_f16 or want_lo):
         out_f16 = torch.empty((M, n_out), dtype=torch.float16, device=a0.device)
+    if out_f16_lo is None and want_lo:
+        out_f16_lo = torch.empty((M, n_out), dtype=torch.float16, device=a0.device)
     if out_f32 is None and want_f32:
         out_f32 = torch.empty((M, n_out), dtype=torch.float32, device=a0.device)
     assert out_f16 is not None or out_f32 is not None
     d = GemmDesc()
-    d.a0, d.a1, d.c0, d.c1 = _ptr(a0), _ptr(a1), c0, c1
+    ptrs = [_ptr(t_) for t_ in srcs] + [None] * (4 - len(srcs))
+    cs = chans + [0] * (4 - len(chans))
+    d.a0, d.a1, d.a2, d.a3 = ptrs
+    d.c0, d.c1, d.c2, d.c3 = cs
     d.nb, d.h, d.w, d.taps = nb, h, w, taps
     d.b, d.n, d.alpha = _ptr(b), n, alpha
     d.bias = _ptr(bias)
@@ -93,7 +101,7 @@ def gemm(a0, b, *, a1=None, nb=None, h=None, w=None, taps=1, bias=None, film=Non
     d.residual = _ptr(residual)
     d.ldr = residual.shape[-1] if residual is not None else 0
     d.act = act
-    d.out_f16, d.out_f32 = _ptr(out_f16), _ptr(out_f32)
+    d.out_f16, d.out_f32, d.out_f16_lo = _ptr(out_f16), _ptr(out_f32), _ptr(out_f16_lo)
     d.ldo = 0
     d.block_n = block_n
     d.splits = splits
@@ -111,6 +119,8 @@ def gemm(a0, b, *, a1=None, nb=None, h=None, w=None, taps=1, bias=None, film=Non
         e1.record()
         PROFILE.append(("gemm", 2.0 * M * n * b.shape[1], e0, e1, (M, n, b.shape[1], taps)))
     _count(2 if splits and splits > 1 else 1)
+    if out_f16_lo is not None:
+        return out_f16, out_f32, out_f16_lo
     return out_f16, out_f32
 
 
@@ -151,11 +161,10 @@ def attention(q, k, vt, *, heads, d, dpad, nq, nkv, scale, causal=False, out=Non
     return out
 
 
-_gn_ws = {}
-
-
-def groupnorm(x0, gamma, beta, *, x1=None, groups=32, eps=1e-5, silu=False, want_raw=False):
-    """x0 (, x1): fp32 NHWC [nb, h, w, c]; returns (normalised fp16 NHWC [nb,h,w,c0+c1], raw fp16 or None)."""
+def groupnorm(x0, gamma, beta, *, x1=None, groups=32, eps=1e-5, silu=False, want_raw=False, want_lo=False,
+              want_raw_lo=False):
+    """x0 (, x1): fp32 NHWC [nb, h, w, c]; returns (normalised fp16 NHWC [nb,h,w,c0+c1], raw fp16 or None), plus the
+    low halves (out_lo, raw_lo) of the hi/lo split when requested: (out, raw, out_lo, raw_lo)."""
     _chk32(x0, "x0")
     nb, h, w, c0 = x0.shape
     c1 = 0
@@ -163,13 +172,16 @@ def groupnorm(x0, gamma, beta, *, x1=None, groups=32, eps=1e-5, silu=False, want
         _chk32(x1, "x1")
         c1 = x1.shape[-1]
     out = torch.empty((nb, h, w, c0 + c1), dtype=torch.float16, device=x0.device)
-    raw = torch.empty_like(out) if want_raw else None
-    key = (x0.device, nb, groups)
+    raw = torch.empty_like(out) if (want_raw or want_raw_lo) else None
+    out_lo = torch.empty_like(out) if want_lo else None
+    raw_lo = torch.empty_like(out) if want_raw_lo else None
     ws = torch.empty(2 * nb * groups, dtype=torch.float64, device=x0.device)
     _l.check(_l.load().sdb_groupnorm(_ptr(x0), _ptr(x1), c0, c1, nb, h * w, groups, _ptr(gamma), _ptr(beta),
-                                     eps, 1 if silu else 0, _ptr(out), _ptr(raw), _ptr(ws), _stream()),
-             "sdb_groupnorm")
+                                     eps, 1 if silu else 0, _ptr(out), _ptr(raw), _ptr(out_lo), _ptr(raw_lo), _ptr(ws),
+                                     _stream()), "sdb_groupnorm")
     _count(3)
+    if want_lo or want_raw_lo:
+        return out, raw, out_lo, raw_lo
     return out, raw
 
 

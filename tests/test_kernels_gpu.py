@@ -219,3 +219,47 @@ def test_elementwise(S, cuda_dev):
     assert float((te.float() - ref).abs().max()) < 2e-3
     tr = S.ops.transpose_f16(o16.reshape(2, 64, 8))
     assert tr.shape == (2, 8, 64) and torch.equal(tr, o16.reshape(2, 64, 8).transpose(1, 2))
+
+
+def test_gemm_hilo_split_recovers_fp32_operands(S, cuda_dev):
+    """[A_hi | A_lo | A_hi] . [W_hi | W_hi | W_lo]: three fp16 passes reproduce the fp32-operand product."""
+    g = torch.Generator().manual_seed(21)
+    M, K, N = 512, 640, 320
+    a = torch.randn(M, K, generator=g).to(cuda_dev) * 3
+    w = (torch.randn(N, K, generator=g) * K ** -0.5).to(cuda_dev)
+    a_hi = a.half()
+    a_lo = (a - a_hi.float()).half()
+    w_hi = w.half()
+    w_lo = (w - w_hi.float()).half()
+    wk = torch.cat([w_hi, w_hi, w_lo], 1).contiguous()
+    _, o3 = S.ops.gemm(a_hi, wk, a1=a_lo, a2=a_hi, want_f32=True)
+    _, o1 = S.ops.gemm(a_hi, w_hi, want_f32=True)
+    ref = a.double() @ w.double().t()
+    assert rel_l2(o3, ref) < 5e-6, rel_l2(o3, ref)
+    assert rel_l2(o1, ref) > 1e-4          # single pass carries the fp16 operand rounding
+    # epilogue hi/lo outputs
+    hi, f32, lo = S.ops.gemm(a_hi, w_hi, want_f32=True, want_lo=True)
+    assert torch.equal(hi, f32.half())
+    assert rel_l2(hi.float() + lo.float(), f32) < 2e-6
+    # groupnorm hi/lo
+    x = torch.randn(2, 8, 8, 128, generator=g).to(cuda_dev)
+    gamma = torch.ones(128, device=cuda_dev)
+    beta = torch.zeros(128, device=cuda_dev)
+    out, raw, out_lo, raw_lo = S.ops.groupnorm(x, gamma, beta, want_lo=True, want_raw_lo=True)
+    ref_n = F.group_norm(x.permute(0, 3, 1, 2), 32, gamma, beta, 1e-5).permute(0, 2, 3, 1)
+    assert rel_l2(out.float() + out_lo.float(), ref_n) < 5e-6
+    assert rel_l2(raw.float() + raw_lo.float(), x) < 1e-6
+
+
+def test_gemm_many_tiles_persistent(S, cuda_dev):
+    """More tiles than SMs: every persistent CTA walks several tiles through both TMEM accumulators."""
+    g = torch.Generator().manual_seed(22)
+    for (M, N, K, bn) in [(128 * 40, 1280, 192, 128), (128 * 37 + 5, 640, 320, 64), (128 * 9, 2560, 128, 256),
+                          (4096, 4096, 512, 0)]:
+        a = _rand16((M, K), cuda_dev, g)
+        b = _rand16((N, K), cuda_dev, g, K ** -0.5)
+        bias = torch.randn(N, generator=g).to(cuda_dev)
+        o16, o32 = S.ops.gemm(a, b, bias=bias, want_f16=True, want_f32=True, block_n=bn)
+        ref = a.double() @ b.double().t() + bias
+        assert rel_l2(o32, ref) < 1e-5, (M, N, K, bn, rel_l2(o32, ref))
+        assert rel_l2(o16.float(), ref) < 6e-4
