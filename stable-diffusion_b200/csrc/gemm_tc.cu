@@ -8,9 +8,11 @@
 //                 B tile [BN x 64] from the K-major weight matrix. STAGES-deep mbarrier ring that runs across tiles.
 //   warp 1      : TMEM allocation + single-thread tcgen05.mma issue (M=128, N=BN, K=16), two accumulator buffers in
 //                 TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
-//   warps 2..5  : epilogue — tcgen05.ld accumulator rows, transpose through padded shared memory so global
-//                 loads/stores are row-contiguous (128 B per 16 lanes), fused alpha/bias/FiLM/residual/activation,
-//                 fp16 (optionally hi+lo pair) and/or fp32 outputs, or raw fp32 split-K partials.
+//   warps 2..9  : epilogue (two warps per TMEM lane group, alternating 32-column chunks) — tcgen05.ld accumulator
+//                 rows (one row per thread), fused alpha/bias/FiLM/residual/activation in registers, 16-byte stores
+//                 into a swizzled staging tile, TMA store (cp.async.bulk.tensor) of each 32x32 block to the NHWC
+//                 output: fp16 (optionally a hi+lo pair) and/or fp32, or raw fp32 split-K partials. Outputs whose row
+//                 pitch TMA cannot address (N = 3, 4 ...) take a scalar transposed path.
 //
 // Replaces cuDNN/cuBLAS calls behind nn.Conv2d / nn.Linear in the reference
 // (ldm/modules/diffusionmodules/openaimodel.py:204,230,241,519,685; ldm/modules/attention.py:40-60,161-168,233-248).
@@ -26,11 +28,17 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int MAX_SRC = 4;
-constexpr int STAGING_BYTES = 4 * 32 * 33 * 4;
+constexpr int EPI_WARPS = 8;
+constexpr int STG_WARP_BYTES = 8192;  // per epilogue warp: 2 x 4 KB fp32 tiles, or 2 x (2 KB hi + 2 KB lo) fp16 tiles
+constexpr int STAGING_BYTES = EPI_WARPS * STG_WARP_BYTES;
+constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
 
 struct TmapPack {
   CUtensorMap a[MAX_SRC];
   CUtensorMap b;
+  CUtensorMap o32;   // fp32 output (or the split-K workspace), 5-D [C, W, H, NB, S], box {32, bw, bh, bn, 1}, SWIZZLE_128B
+  CUtensorMap o16;   // fp16 output, same geometry, SWIZZLE_64B
+  CUtensorMap o16lo; // fp16 low half
 };
 
 struct GemmArgs {
@@ -54,6 +62,8 @@ struct GemmArgs {
   int ldo;
   float* ws;
   int act;
+  int fast;         // outputs go through the TMA-store epilogue
+  int bw, bh;       // store box: bw x bh x (32 / (bw*bh)) output pixels per epilogue warp
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
@@ -169,21 +179,22 @@ __device__ __forceinline__ void drain_chunk(const GemmArgs& p, const float* stag
 
 template <int BN>
 struct GemmCfg {
-  static constexpr int STAGES = BN <= 32 ? 8 : BN <= 64 ? 8 : BN <= 128 ? 6 : BN <= 160 ? 5 : 4;
+  static constexpr int STAGES = BN <= 32 ? 6 : BN <= 64 ? 6 : BN <= 128 ? 4 : BN <= 160 ? 4 : 3;
   static constexpr int TMEM_COLS = BN <= 32 ? 64 : BN <= 64 ? 128 : BN <= 128 ? 256 : 512;  // two accumulators
   static constexpr int SMEM = STAGES * (A_BYTES + BN * BK * 2) + STAGING_BYTES + 1024;
 };
 
 template <int BN>
-__global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__ TmapPack tm, const GemmArgs p) {
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TmapPack tm, const GemmArgs p) {
   constexpr int STAGES = GemmCfg<BN>::STAGES;
   constexpr int B_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr int TMEM_COLS = GemmCfg<BN>::TMEM_COLS;
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* staging = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+  // 1024-byte alignment by offset (keeps the shared address space visible to the compiler: LDS/STS, not generic)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* staging = smem + STAGES * STAGE_BYTES;
   __shared__ uint64_t full_bar[STAGES];
   __shared__ uint64_t empty_bar[STAGES];
   __shared__ uint64_t acc_full[2];
@@ -197,13 +208,18 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < p.nsrc; ++i) tma_prefetch_desc(&tm.a[i]);
     tma_prefetch_desc(&tm.b);
+    if (p.fast) {
+      if (p.out_f32 || p.ws) tma_prefetch_desc(&tm.o32);
+      if (p.out_f16) tma_prefetch_desc(&tm.o16);
+      if (p.out_f16_lo) tma_prefetch_desc(&tm.o16lo);
+    }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 4);
+      mbar_init(&acc_empty[i], EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -288,9 +304,21 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
       }
     }
   } else {
-    // epilogue warps 2..5 : TMEM lane group = warp % 4
+    // epilogue warps 2..9 : TMEM lane group = warp % 4; the two warps of a lane group alternate chunks
+    const int ew = warp - 2;
     const int lg = warp & 3;
-    float* stage = staging + lg * (32 * 33);
+    const int par = ew >> 2;
+    uint8_t* stg = staging + ew * STG_WARP_BYTES;
+    float* stage = reinterpret_cast<float*>(stg);  // scalar path: [32][33] floats
+    const bool geglu = (p.act == SDB_ACT_GEGLU) && !p.ws;
+    constexpr int HALF = BN / 2;
+    const int n_chunks = geglu ? HALF / 32 : BN / 32;
+    const bool st32 = p.ws || p.out_f32;
+    const bool st16 = !p.ws && p.out_f16;
+    const bool st16lo = st16 && p.out_f16_lo;
+    // staging buffers per chunk parity: fp32 tiles 4 KB each; fp16 hi 2 KB + lo 2 KB each (fp32+fp16 together: single)
+    const bool dbl = !(st32 && st16);
+    uint32_t flip = 0;
     uint32_t local = 0;
     for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x, ++local) {
       const int m_tile = tile % p.m_tiles;
@@ -299,24 +327,37 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
       const int split = rest / p.n_tiles;
       const uint32_t ab = local & 1;
       int my_row;
-      const bool my_valid = map_row(p, m_tile, lg * 32 + lane, my_row);
+      const int r_tile = lg * 32 + lane;
+      const bool my_valid = map_row(p, m_tile, r_tile, my_row);
       const int my_sample = my_valid ? my_row / p.rows_per_sample : 0;
+      // store-box origin of this warp's 32 rows
+      int sx, sy, sn;
+      if (p.taps == 1) {
+        sx = m_tile * BM + lg * 32;
+        sy = 0;
+        sn = 0;
+      } else {
+        const int tx = m_tile % p.tiles_x;
+        const int t2 = m_tile / p.tiles_x;
+        const int r0 = lg * 32;
+        sx = tx * p.TW + r0 % p.TW;
+        sy = (t2 % p.tiles_y) * p.TH + (r0 / p.TW) % p.TH;
+        sn = (t2 / p.tiles_y) * p.TN + r0 / (p.TW * p.TH);
+      }
       mbar_wait(&acc_full[ab], (local >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_d + ab * BN + (static_cast<uint32_t>(lg * 32) << 16);
-      if (p.act == SDB_ACT_GEGLU && !p.ws) {
-        constexpr int HALF = BN / 2;
+      int last_c = -1;
+      for (int c = par; c < n_chunks; c += 2) last_c = c;
 #pragma unroll 1
-        for (int c = 0; c < HALF / 32; ++c) {
+      for (int c = par; c < n_chunks; c += 2) {
+        float v[32];
+        int ocol0;
+        if (geglu) {
           uint32_t xr[32], gr[32];
           tmem_ld32(taddr + c * 32, xr);
           tmem_ld32(taddr + HALF + c * 32, gr);
           tmem_ld_wait();
-          if (c == HALF / 32 - 1) {  // accumulator fully read: hand the buffer back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[ab]);
-          }
           const int colx = n_tile * BN + c * 32;  // accumulator column of the value half; gate at +HALF
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -326,31 +367,132 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
               x += __ldg(p.bias + colx + j);
               g += __ldg(p.bias + colx + HALF + j);
             }
-            stage[lane * 33 + j] = x * gelu_erf(g);
+            v[j] = x * gelu_erf(g);
           }
-          __syncwarp();
-          drain_chunk(p, stage, lane, my_row, my_sample, my_valid, n_tile * HALF + c * 32, p.N / 2, 2, split);
-          __syncwarp();
-        }
-      } else {
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+          ocol0 = n_tile * HALF + c * 32;
+        } else {
           uint32_t rr[32];
           tmem_ld32(taddr + c * 32, rr);
           tmem_ld_wait();
-          if (c == BN / 32 - 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[ab]);
-          }
 #pragma unroll
-          for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(rr[j]);
-          __syncwarp();
-          drain_chunk(p, stage, lane, my_row, my_sample, my_valid, n_tile * BN + c * 32, p.N, p.ws ? 1 : 0, split);
-          __syncwarp();
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
+          ocol0 = n_tile * BN + c * 32;
         }
+        if (c == last_c) {  // accumulator fully read by this warp: hand the buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[ab]);
+        }
+        if (!p.fast) {
+          // scalar transposed path (row pitch not TMA-addressable)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = v[j];
+          __syncwarp();
+          drain_chunk(p, stage, lane, my_row, my_sample, my_valid, ocol0, geglu ? p.N / 2 : p.N, geglu ? 2 : (p.ws ? 1 : 0),
+                      split);
+          __syncwarp();
+          continue;
+        }
+        if (!geglu && !p.ws) {
+          // fused epilogue in row-per-thread layout; all pointers are 16-byte aligned on this path
+          if (p.bias) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + ocol0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float4 t = __ldg(bp + q);
+              v[4 * q] = v[4 * q] * p.alpha + t.x;
+              v[4 * q + 1] = v[4 * q + 1] * p.alpha + t.y;
+              v[4 * q + 2] = v[4 * q + 2] * p.alpha + t.z;
+              v[4 * q + 3] = v[4 * q + 3] * p.alpha + t.w;
+            }
+          } else if (p.alpha != 1.0f) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+          }
+          if (p.film) {
+            const float4* fp = reinterpret_cast<const float4*>(p.film + static_cast<size_t>(my_sample) * p.ldf + ocol0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float4 t = __ldg(fp + q);
+              v[4 * q] += t.x;
+              v[4 * q + 1] += t.y;
+              v[4 * q + 2] += t.z;
+              v[4 * q + 3] += t.w;
+            }
+          }
+          if (p.residual && my_valid) {
+            const float4* rp = reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(my_row) * p.ldr + ocol0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float4 t = rp[q];
+              v[4 * q] += t.x;
+              v[4 * q + 1] += t.y;
+              v[4 * q + 2] += t.z;
+              v[4 * q + 3] += t.w;
+            }
+          }
+          if (p.act != SDB_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+          }
+        }
+        // staging buffer for this chunk; make sure the TMA store that last read it has finished reading
+        const uint32_t bsel = dbl ? (flip & 1) : 0;
+        if (lane == 0) {
+          if (dbl) tma_store_wait_read<1>();
+          else tma_store_wait_read<0>();
+        }
+        __syncwarp();
+        uint8_t* s32 = stg + bsel * 4096;
+        uint8_t* s16 = st32 ? stg + 4096 : stg + bsel * 4096;
+        uint8_t* s16l = s16 + 2048;
+        if (st32) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(s32 + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+                make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+        if (st16) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            __half2 h[4];
+            uint4 u, ul;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[8 * q + 2 * e], v[8 * q + 2 * e + 1]);
+            u.x = *reinterpret_cast<uint32_t*>(&h[0]);
+            u.y = *reinterpret_cast<uint32_t*>(&h[1]);
+            u.z = *reinterpret_cast<uint32_t*>(&h[2]);
+            u.w = *reinterpret_cast<uint32_t*>(&h[3]);
+            const uint32_t off = lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4);
+            *reinterpret_cast<uint4*>(s16 + off) = u;
+            if (st16lo) {
+              __half2 l[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float2 hf = __half22float2(h[e]);
+                l[e] = __floats2half2_rn(v[8 * q + 2 * e] - hf.x, v[8 * q + 2 * e + 1] - hf.y);
+              }
+              ul.x = *reinterpret_cast<uint32_t*>(&l[0]);
+              ul.y = *reinterpret_cast<uint32_t*>(&l[1]);
+              ul.z = *reinterpret_cast<uint32_t*>(&l[2]);
+              ul.w = *reinterpret_cast<uint32_t*>(&l[3]);
+              *reinterpret_cast<uint4*>(s16l + off) = ul;
+            }
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          const int s4 = p.ws ? split : 0;
+          if (st32) tma_store_5d(&tm.o32, s32, ocol0, sx, sy, sn, s4);
+          if (st16) tma_store_5d(&tm.o16, s16, ocol0, sx, sy, sn, 0);
+          if (st16lo) tma_store_5d(&tm.o16lo, s16l, ocol0, sx, sy, sn, 0);
+          tma_store_commit();
+        }
+        ++flip;
       }
     }
+    if (lane == 0) tma_store_wait<0>();
     tc_fence_before();
   }
   __syncthreads();
@@ -405,7 +547,7 @@ static int launch_gemm(const TmapPack& tm, const GemmArgs& p, cudaStream_t st) {
   }
   const int tiles = p.m_tiles * p.n_tiles * p.splits;
   const int grid = std::min(tiles, sm_count());
-  kern<<<grid, 192, Cfg::SMEM, st>>>(tm, p);
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM, st>>>(tm, p);
   SDB_LAUNCH_CHECK();
   return 0;
 }
@@ -585,6 +727,53 @@ extern "C" int sdb_gemm(const sdb_gemm_desc* d, sdb_stream_t stream) {
     uint64_t str[1] = {K * 2};
     uint32_t box[2] = {64, static_cast<uint32_t>(bn)};
     if (make_tmap_f16(&tm.b, d->b, 2, dims, str, box)) return 1;
+  }
+  // output maps for the TMA-store epilogue (fast path); otherwise the scalar transposed path is used
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  bool fast = (n_out % 32 == 0) && (p.ldo % 8 == 0) && (!p.bias || al16(p.bias)) &&
+              (!p.film || (al16(p.film) && p.ldf % 4 == 0)) && (!p.residual || (al16(p.residual) && p.ldr % 4 == 0)) &&
+              (!p.out_f32 || al16(p.out_f32)) && (!p.out_f16 || al16(p.out_f16)) &&
+              (!p.out_f16_lo || al16(p.out_f16_lo)) && (!p.ws || (d->n % 32 == 0 && al16(p.ws)));
+  p.fast = fast ? 1 : 0;
+  p.bw = d->taps == 1 ? 32 : std::min(p.TW, 32);
+  p.bh = d->taps == 1 ? 1 : std::min(p.TH, 32 / p.bw);
+  tm.o32 = tm.b;
+  tm.o16 = tm.b;
+  tm.o16lo = tm.b;
+  if (fast) {
+    const uint32_t bnn = static_cast<uint32_t>(32 / (p.bw * p.bh));
+    auto make_out = [&](CUtensorMap* m, const void* base, int elem, int ncols, long ld, int nsplit) -> int {
+      uint64_t e = static_cast<uint64_t>(elem);
+      uint64_t pitch = static_cast<uint64_t>(ld) * e;
+      uint64_t dims[5], str[4];
+      uint32_t box[5] = {32, static_cast<uint32_t>(p.bw), static_cast<uint32_t>(p.bh), bnn, 1};
+      dims[0] = static_cast<uint64_t>(ncols);
+      if (d->taps == 1) {
+        dims[1] = static_cast<uint64_t>(M);
+        dims[2] = 1;
+        dims[3] = 1;
+        str[0] = pitch;
+        str[1] = pitch * M;
+        str[2] = pitch * M;
+      } else {
+        dims[1] = static_cast<uint64_t>(d->w);
+        dims[2] = static_cast<uint64_t>(d->h);
+        dims[3] = static_cast<uint64_t>(d->nb);
+        str[0] = pitch;
+        str[1] = pitch * d->w;
+        str[2] = pitch * d->w * d->h;
+      }
+      dims[4] = static_cast<uint64_t>(nsplit);
+      str[3] = pitch * M;
+      return make_tmap(m, base, elem, elem == 4 ? 128 : 64, 5, dims, str, box);
+    };
+    if (p.ws) {
+      if (make_out(&tm.o32, p.ws, 4, d->n, d->n, splits)) return 1;
+    } else {
+      if (p.out_f32 && make_out(&tm.o32, p.out_f32, 4, n_out, p.ldo, 1)) return 1;
+      if (p.out_f16 && make_out(&tm.o16, p.out_f16, 2, n_out, p.ldo, 1)) return 1;
+      if (p.out_f16_lo && make_out(&tm.o16lo, p.out_f16_lo, 2, n_out, p.ldo, 1)) return 1;
+    }
   }
 
   int rc;

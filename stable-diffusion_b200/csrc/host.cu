@@ -34,10 +34,11 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                  const uint32_t* box) {
+int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int swizzle_bytes, int rank, const uint64_t* dims,
+              const uint64_t* strides_bytes, const uint32_t* box) {
   EncodeTiledFn fn = encode_fn();
   SDB_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+  SDB_CHECK(rank >= 1 && rank <= 5, "TMA rank %d", rank);
   cuuint64_t gdim[5], gstr[5];
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) {
@@ -49,15 +50,24 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
   SDB_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base %p not 16-byte aligned", base);
   for (int i = 0; i + 1 < rank; ++i)
     SDB_CHECK((gstr[i] & 15) == 0, "TMA stride[%d]=%llu not a multiple of 16 bytes", i, (unsigned long long)gstr[i]);
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUtensorMapDataType dt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(out, dt, rank, const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SDB_CHECK(r == CUDA_SUCCESS,
-            "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu,%llu,%llu,%llu] box [%u,%u,%u,%u]", (int)r, rank,
-            (unsigned long long)gdim[0], (unsigned long long)(rank > 1 ? gdim[1] : 0),
-            (unsigned long long)(rank > 2 ? gdim[2] : 0), (unsigned long long)(rank > 3 ? gdim[3] : 0), bx[0],
-            rank > 1 ? bx[1] : 0, rank > 2 ? bx[2] : 0, rank > 3 ? bx[3] : 0);
+            "cuTensorMapEncodeTiled failed (%d): rank %d elem %d dims [%llu,%llu,%llu,%llu,%llu] box [%u,%u,%u,%u,%u]",
+            (int)r, rank, elem_bytes, (unsigned long long)gdim[0], (unsigned long long)(rank > 1 ? gdim[1] : 0),
+            (unsigned long long)(rank > 2 ? gdim[2] : 0), (unsigned long long)(rank > 3 ? gdim[3] : 0),
+            (unsigned long long)(rank > 4 ? gdim[4] : 0), bx[0], rank > 1 ? bx[1] : 0, rank > 2 ? bx[2] : 0,
+            rank > 3 ? bx[3] : 0, rank > 4 ? bx[4] : 0);
   return 0;
+}
+
+int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box) {
+  return make_tmap(out, base, 2, 128, rank, dims, strides_bytes, box);
 }
 
 static long long g_launches = 0;
