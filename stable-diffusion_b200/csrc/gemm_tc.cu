@@ -349,6 +349,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       const uint32_t taddr = tmem_d + ab * BN + (static_cast<uint32_t>(lg * 32) << 16);
       int last_c = -1;
       for (int c = par; c < n_chunks; c += 2) last_c = c;
+      if (last_c < 0) {  // BN = 32: the odd-parity warps own no chunk but still take part in the hand-off
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[ab]);
+      }
 #pragma unroll 1
       for (int c = par; c < n_chunks; c += 2) {
         float v[32];

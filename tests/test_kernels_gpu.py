@@ -263,3 +263,14 @@ def test_gemm_many_tiles_persistent(S, cuda_dev):
         ref = a.double() @ b.double().t() + bias
         assert rel_l2(o32, ref) < 1e-5, (M, N, K, bn, rel_l2(o32, ref))
         assert rel_l2(o16.float(), ref) < 6e-4
+
+
+def test_gemm_narrow_tiles_many_per_cta(S, cuda_dev):
+    """block_n 32/64 with more than two tiles per persistent CTA (accumulator hand-off with idle epilogue warps)."""
+    g = torch.Generator().manual_seed(23)
+    for (M, N, K, bn) in [(128 * 500, 32, 128, 32), (128 * 300, 96, 64, 32), (128 * 450, 64, 192, 64), (128 * 700, 3, 128, 0)]:
+        a = _rand16((M, K), cuda_dev, g)
+        b = _rand16((N, K), cuda_dev, g, K ** -0.5)
+        _, o32 = S.ops.gemm(a, b, want_f32=True, block_n=bn)
+        ref = a.double() @ b.double().t()
+        assert rel_l2(o32, ref) < 1e-5, (M, N, K, bn)
