@@ -150,23 +150,9 @@ def run_gpu(args):
     model = pipeline.build_model()
     pipeline.load_random_weights(model, dev, gen_device=dev)   # same seeds on every rank -> identical weights
     if world > 1:
-        # NCCL broadcast of the packed weight arena from rank 0 over NVLink: one collective per stage
-        for W in (model.model.diffusion_model.W, model.first_stage_model.W, model.cond_stage_model.W):
-            flat = []
-
-            def walk(o):
-                if torch.is_tensor(o):
-                    flat.append(o)
-                elif isinstance(o, dict):
-                    [walk(v) for v in o.values()]
-                elif isinstance(o, (list, tuple)):
-                    [walk(v) for v in o]
-            walk(W)
-            seen = set()
-            for t in flat:
-                if t.data_ptr() not in seen and t.is_cuda:
-                    seen.add(t.data_ptr())
-                    dist.broadcast(t, src=0)
+        # NCCL broadcast of the packed weights from rank 0 over NVLink instead of N host loads
+        sdb200.dist.broadcast_weights(model.model.diffusion_model.W, model.first_stage_model.W,
+                                      model.cond_stage_model.W, src=0)
     pipe = pipeline.Txt2Img(model, sampler="plms", steps=50, scale=7.5, height=512, width=512, cuda_graph=True)
 
     # synthetic inputs: seeded token ids (BOS + tokens + EOS padding) and start noise, per global sample index
@@ -176,7 +162,8 @@ def run_gpu(args):
     ids_h[:, 20:] = 49407
     un_h = torch.full((B, 77), 49407, dtype=torch.long)
     un_h[:, 0] = 49406
-    xT_h = torch.randn(B, 4, 64, 64, generator=torch.Generator().manual_seed(42 + rank))
+    lo, hi = sdb200.dist.shard_range(B * world, rank, world)
+    xT_h = sdb200.dist.batch_noise(lo, hi, (4, 64, 64), seed=42)   # per GLOBAL sample index: world-size independent
     ids_p, un_p, xT_p = ids_h.pin_memory(), un_h.pin_memory(), xT_h.pin_memory()
     out_h = torch.empty((B, 512, 512, 3), dtype=torch.uint8).pin_memory()
     ids_d, un_d, xT_d = ids_h.to(dev), un_h.to(dev), xT_h.to(dev)

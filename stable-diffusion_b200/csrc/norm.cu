@@ -148,8 +148,8 @@ __global__ void __launch_bounds__(GN_THREADS)
   }
 }
 
-// LayerNorm: one warp per row, row held in registers (C <= 32*LN_MAX_PER_LANE).
-constexpr int LN_MAX_PER_LANE = 48;
+// LayerNorm: one warp per row, row held in registers (NPL = ceil(C / 32) elements per lane, compile-time).
+template <int NPL>
 __global__ void __launch_bounds__(256)
     layernorm_kernel(const float* __restrict__ x, int rows, int C, const float* __restrict__ gamma,
                      const float* __restrict__ beta, float eps, __half* __restrict__ out, float* __restrict__ out32) {
@@ -157,10 +157,10 @@ __global__ void __launch_bounds__(256)
   int lane = threadIdx.x & 31;
   if (warp >= rows) return;
   const float* p = x + static_cast<size_t>(warp) * C;
-  float v[LN_MAX_PER_LANE];
+  float v[NPL];
   float s = 0.f;
 #pragma unroll
-  for (int j = 0; j < LN_MAX_PER_LANE; ++j) {
+  for (int j = 0; j < NPL; ++j) {
     int c = lane + j * 32;
     v[j] = c < C ? p[c] : 0.f;
     s += v[j];
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(256)
   float mean = s / C;
   float q = 0.f;
 #pragma unroll
-  for (int j = 0; j < LN_MAX_PER_LANE; ++j) {
+  for (int j = 0; j < NPL; ++j) {
     int c = lane + j * 32;
     float d = c < C ? v[j] - mean : 0.f;
     q += d * d;
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(256)
   for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
   float rstd = rsqrtf(q / C + eps);
 #pragma unroll
-  for (int j = 0; j < LN_MAX_PER_LANE; ++j) {
+  for (int j = 0; j < NPL; ++j) {
     int c = lane + j * 32;
     if (c < C) {
       float y = (v[j] - mean) * rstd * gamma[c] + beta[c];
@@ -236,9 +236,11 @@ extern "C" int sdb_groupnorm(const float* x0, const float* x1, int32_t c0, int32
   int cw = GN_THREADS;
   while (cw > 32 && cw / 2 >= C) cw /= 2;
   const int rstep = GN_THREADS / cw;
-  // enough blocks to fill the machine (a few waves), at least `rstep` rows per block
+  // one wave of blocks: every block ends with 2*groups fp64 atomics on the same few addresses, so more blocks only
+  // add contention (measured: 586 blocks -> 26 us, of which ~20 us atomics)
   int target_blocks = sm_count() * 4;
-  int slabs = std::max(1, std::min((hw + rstep - 1) / rstep, (target_blocks + nb - 1) / nb));
+  int stats_blocks = sm_count();
+  int slabs = std::max(1, std::min((hw + 4 * rstep - 1) / (4 * rstep), (stats_blocks + nb - 1) / nb));
   int rows_per_block = (hw + slabs - 1) / slabs;
   slabs = (hw + rows_per_block - 1) / rows_per_block;
   dim3 grid(slabs, nb);
@@ -262,11 +264,20 @@ extern "C" int sdb_layernorm(const float* x, int32_t rows, int32_t c, const floa
                              void* out_f16, float* out_f32, sdb_stream_t stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SDB_CHECK(x && gamma && beta && (out_f16 || out_f32), "sdb_layernorm: null pointer");
-  SDB_CHECK(c <= 32 * LN_MAX_PER_LANE, "sdb_layernorm: C=%d too large", c);
+  SDB_CHECK(c <= 32 * 48, "sdb_layernorm: C=%d too large", c);
   int warps_per_block = 8;
   int blocks = (rows + warps_per_block - 1) / warps_per_block;
-  layernorm_kernel<<<blocks, warps_per_block * 32, 0, st>>>(x, rows, c, gamma, beta, eps,
-                                                            static_cast<__half*>(out_f16), out_f32);
+  __half* o16 = static_cast<__half*>(out_f16);
+  const int npl = (c + 31) / 32;
+#define SDB_LN(N) layernorm_kernel<N><<<blocks, warps_per_block * 32, 0, st>>>(x, rows, c, gamma, beta, eps, o16, out_f32)
+  if (npl <= 2) SDB_LN(2);
+  else if (npl <= 4) SDB_LN(4);
+  else if (npl <= 10) SDB_LN(10);
+  else if (npl <= 20) SDB_LN(20);
+  else if (npl <= 24) SDB_LN(24);
+  else if (npl <= 40) SDB_LN(40);
+  else SDB_LN(48);
+#undef SDB_LN
   SDB_LAUNCH_CHECK();
   return 0;
 }

@@ -1,0 +1,67 @@
+"""The C-ABI library loads without a GPU and exports exactly the symbols include/sdb200.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from helpers import ROOT
+import sdb200
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "sdb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sdb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = sdb200.lib.load()
+    syms = _header_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/sdb200.h but not exported"
+    assert sorted(sdb200.lib.SIGNATURES) == syms, (set(sdb200.lib.SIGNATURES) ^ set(syms))
+
+
+def test_version_and_error_string_without_gpu():
+    lib = sdb200.lib.load()
+    assert lib.sdb_version() >= 100
+    assert isinstance(lib.sdb_last_error(), bytes)
+    assert lib.sdb_launch_count() >= 0
+
+
+def test_struct_layouts_match_header():
+    """ctypes mirrors of sdb_gemm_desc / sdb_attn_desc: field order and count as declared in the header."""
+    text = open(os.path.join(ROOT, "include", "sdb200.h")).read()
+
+    def fields(name):
+        body = re.search(r"typedef struct " + name + r" \{(.*?)\} " + name + ";", text, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        out = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            names = decl.replace("*", " ").split()
+            # "int32_t c0, c1, c2, c3" -> several names
+            first = [n for n in names if n not in ("const", "void", "float", "int32_t", "int64_t")]
+            out += [n.strip(",") for n in first]
+        return out
+
+    assert fields("sdb_gemm_desc") == [f[0] for f in sdb200.lib.GemmDesc._fields_]
+    assert fields("sdb_attn_desc") == [f[0] for f in sdb200.lib.AttnDesc._fields_]
+    assert ctypes.sizeof(sdb200.lib.GemmDesc) % 8 == 0
+
+
+def test_product_path_fails_loudly_without_cuda():
+    """No CPU fallback anywhere: CPU tensors are rejected, not silently computed with torch."""
+    from sdb200 import arch
+    net = sdb200.UNetModel(**arch.TINY_UNET)
+    net._host_sd = None
+    with pytest.raises((AssertionError, RuntimeError)):
+        net(torch.zeros(1, 4, 16, 16), torch.zeros(1), context=torch.zeros(1, 77, 64))
+    if not torch.cuda.is_available():
+        with pytest.raises(Exception):
+            sdb200.ops.cast_f16(torch.zeros(4))
