@@ -75,6 +75,9 @@ typedef struct sdb_gemm_desc {
                             bounded by workspace_floats); split-K needs workspace of splits*M*n floats */
   float* workspace;
   int64_t workspace_floats;
+  void* stats_out;       /* optional fp64 [M / rows_per_sample, n, 2]: per-(sample, channel) sum and sum of squares of
+                            the fp32 output, accumulated by the epilogue (zeroed by the call) — the GroupNorm statistics
+                            of the tensor being produced, so no separate reduction pass reads it again */
 } sdb_gemm_desc;
 
 int sdb_gemm(const sdb_gemm_desc* d, sdb_stream_t stream);
@@ -107,14 +110,16 @@ int sdb_attention(const sdb_attn_desc* d, sdb_stream_t stream);
 /*
  * GroupNorm(32) [+ SiLU] over NHWC fp32 input that may be the channel concat of two tensors
  * (ldm/modules/diffusionmodules/util.py:199-216 GroupNorm32 in fp32; attention.py:76-77 Normalize eps 1e-6;
- * model.py:38-39). Statistics in fp32 (two-pass, per (sample, group)). Writes the normalised fp16 operand
+ * model.py:38-39). Statistics: fp32 per-block partials, folded in fp64 by the last block of each sample. Writes the normalised fp16 operand
  * for the following conv and optionally a raw fp16 cast of the (concatenated) input for the 1x1 skip conv.
  */
 int sdb_groupnorm(const float* x0, const float* x1, int32_t c0, int32_t c1, int32_t nb, int32_t hw, int32_t groups,
                   const float* gamma, const float* beta, float eps, int32_t silu, void* out_f16, void* raw_f16,
                   void* out_lo_f16 /* optional low half of the normalised output (hi/lo split) */,
                   void* raw_lo_f16 /* optional low half of the raw cast */,
-                  void* stats_ws /* 2*nb*groups doubles, zeroed by the call */, sdb_stream_t stream);
+                  void* stats_ws /* scratch: nb * (128*groups*2 + groups*2 + 1) * 4 bytes */,
+                  const void* chan_stats0 /* optional fp64 [nb, c0, 2] from sdb_gemm.stats_out (skips the stats pass) */,
+                  const void* chan_stats1 /* same for x1 */, sdb_stream_t stream);
 
 /* LayerNorm over the last dim of fp32 [rows, c] -> fp16 (attention.py:203-205, eps 1e-5). */
 int sdb_layernorm(const float* x, int32_t rows, int32_t c, const float* gamma, const float* beta, float eps,

@@ -26,6 +26,12 @@ struct AttnArgs {
   int causal;
 };
 
+__device__ __forceinline__ float fast_exp2(float x) {  // one MUFU.EX2, flush-to-zero (exp2(-inf) = 0)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <int DPAD>
 __global__ void __launch_bounds__(192)
     attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -39,7 +45,8 @@ __global__ void __launch_bounds__(192)
   constexpr uint32_t O_COL = 128;
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by offset (keeps the shared address space visible to the compiler: STS, not generic ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* q_s = smem;
   uint8_t* k_s = q_s + Q_BYTES;        // 2 stages
   uint8_t* v_s = k_s + 2 * K_BYTES;    // 2 stages
@@ -147,7 +154,7 @@ __global__ void __launch_bounds__(192)
       const int s = j & 1;
       mbar_wait(&s_full[s], (j >> 1) & 1);
       tc_fence_after();
-      float t[AKV];
+      float t[AKV];  // raw scores q.k (unscaled); the softmax scale is folded into one FFMA per element below
       {
         uint32_t r0[32], r1[32];
         tmem_ld32(tmem + lane_addr + s * AKV, r0);
@@ -155,19 +162,23 @@ __global__ void __launch_bounds__(192)
         tmem_ld_wait();
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
-          t[c] = __uint_as_float(r0[c]) * p.scale_log2;
-          t[32 + c] = __uint_as_float(r1[c]) * p.scale_log2;
+          t[c] = __uint_as_float(r0[c]);
+          t[32 + c] = __uint_as_float(r1[c]);
         }
       }
       const int kv0 = j * AKV;
-      float m_blk = -INFINITY;
+      // only the ragged last block and (causal) diagonal blocks need per-element masking
+      if ((kv0 + AKV > p.nkv) || (p.causal && kv0 + AKV - 1 > q0)) {
 #pragma unroll
-      for (int c = 0; c < AKV; ++c) {
-        int kv = kv0 + c;
-        bool masked = (kv >= p.nkv) || (p.causal && kv > qi);
-        if (masked) t[c] = -INFINITY;
-        m_blk = fmaxf(m_blk, t[c]);
+        for (int c = 0; c < AKV; ++c) {
+          int kv = kv0 + c;
+          if ((kv >= p.nkv) || (p.causal && kv > qi)) t[c] = -INFINITY;
+        }
       }
+      float m_raw = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < AKV; ++c) m_raw = fmaxf(m_raw, t[c]);
+      const float m_blk = m_raw * p.scale_log2;  // scale > 0
       if (j == 0) {
         m_used = m_blk;
       } else {
@@ -193,9 +204,10 @@ __global__ void __launch_bounds__(192)
         }
       }
       float sum = 0.f;
+      const float neg_m = -m_used;
 #pragma unroll
       for (int c = 0; c < AKV; ++c) {
-        t[c] = exp2f(t[c] - m_used);
+        t[c] = fast_exp2(fmaf(t[c], p.scale_log2, neg_m));
         sum += t[c];
       }
       l += sum;

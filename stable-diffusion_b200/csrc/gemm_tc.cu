@@ -39,6 +39,7 @@ struct TmapPack {
   CUtensorMap o32;   // fp32 output (or the split-K workspace), 5-D [C, W, H, NB, S], box {32, bw, bh, bn, 1}, SWIZZLE_128B
   CUtensorMap o16;   // fp16 output, same geometry, SWIZZLE_64B
   CUtensorMap o16lo; // fp16 low half
+  CUtensorMap ows;   // split-K fp32 partial planes [C, W, H, NB, splits]
 };
 
 struct GemmArgs {
@@ -62,6 +63,8 @@ struct GemmArgs {
   int ldo;
   float* ws;
   int act;
+  double* stats;    // optional per-(sample, channel) {sum, sum of squares} of the fp32 output (GroupNorm statistics)
+  unsigned int* tickets;  // split-K: one arrival counter per output tile (self-resetting)
   int fast;         // outputs go through the TMA-store epilogue
   int bw, bh;       // store box: bw x bh x (32 / (bw*bh)) output pixels per epilogue warp
 };
@@ -200,6 +203,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   __shared__ uint64_t acc_full[2];
   __shared__ uint64_t acc_empty[2];
   __shared__ uint32_t tmem_base_smem;
+  __shared__ uint32_t ticket_flag_smem;
+  uint32_t* ticket_flag = &ticket_flag_smem;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -209,7 +214,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     for (int i = 0; i < p.nsrc; ++i) tma_prefetch_desc(&tm.a[i]);
     tma_prefetch_desc(&tm.b);
     if (p.fast) {
-      if (p.out_f32 || p.ws) tma_prefetch_desc(&tm.o32);
+      if (p.ws) tma_prefetch_desc(&tm.ows);
+      if (p.out_f32) tma_prefetch_desc(&tm.o32);
       if (p.out_f16) tma_prefetch_desc(&tm.o16);
       if (p.out_f16_lo) tma_prefetch_desc(&tm.o16lo);
     }
@@ -313,9 +319,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     const bool geglu = (p.act == SDB_ACT_GEGLU) && !p.ws;
     constexpr int HALF = BN / 2;
     const int n_chunks = geglu ? HALF / 32 : BN / 32;
-    const bool st32 = p.ws || p.out_f32;
-    const bool st16 = !p.ws && p.out_f16;
-    const bool st16lo = st16 && p.out_f16_lo;
+    const bool st32 = p.ws || p.out_f32;   // an fp32 tile is staged in some phase (output or split-K partial)
+    const bool st16 = p.out_f16 != nullptr;
     // staging buffers per chunk parity: fp32 tiles 4 KB each; fp16 hi 2 KB + lo 2 KB each (fp32+fp16 together: single)
     const bool dbl = !(st32 && st16);
     uint32_t flip = 0;
@@ -354,52 +359,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[ab]);
       }
-#pragma unroll 1
-      for (int c = par; c < n_chunks; c += 2) {
-        float v[32];
-        int ocol0;
-        if (geglu) {
-          uint32_t xr[32], gr[32];
-          tmem_ld32(taddr + c * 32, xr);
-          tmem_ld32(taddr + HALF + c * 32, gr);
-          tmem_ld_wait();
-          const int colx = n_tile * BN + c * 32;  // accumulator column of the value half; gate at +HALF
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(xr[j]) * p.alpha;
-            float g = __uint_as_float(gr[j]) * p.alpha;
-            if (p.bias) {
-              x += __ldg(p.bias + colx + j);
-              g += __ldg(p.bias + colx + HALF + j);
-            }
-            v[j] = x * gelu_erf(g);
-          }
-          ocol0 = n_tile * HALF + c * 32;
-        } else {
-          uint32_t rr[32];
-          tmem_ld32(taddr + c * 32, rr);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
-          ocol0 = n_tile * BN + c * 32;
-        }
-        if (c == last_c) {  // accumulator fully read by this warp: hand the buffer back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[ab]);
-        }
-        if (!p.fast) {
-          // scalar transposed path (row pitch not TMA-addressable)
-#pragma unroll
-          for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = v[j];
-          __syncwarp();
-          drain_chunk(p, stage, lane, my_row, my_sample, my_valid, ocol0, geglu ? p.N / 2 : p.N, geglu ? 2 : (p.ws ? 1 : 0),
-                      split);
-          __syncwarp();
-          continue;
-        }
-        if (!geglu && !p.ws) {
-          // fused epilogue in row-per-thread layout; all pointers are 16-byte aligned on this path
+      // ---- fused epilogue + staging + TMA store of one 32x32 chunk held in registers (row per thread)
+      auto emit = [&](float (&v)[32], int ocol0, bool fuse, bool raw_partial) {
+        if (fuse) {
+          // all pointers are 16-byte aligned on this path
           if (p.bias) {
             const float4* bp = reinterpret_cast<const float4*>(p.bias + ocol0);
 #pragma unroll
@@ -441,6 +404,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
           }
         }
+        const bool w32 = raw_partial || p.out_f32;
+        const bool w16 = !raw_partial && p.out_f16;
+        const bool w16lo = w16 && p.out_f16_lo;
         // staging buffer for this chunk; make sure the TMA store that last read it has finished reading
         const uint32_t bsel = dbl ? (flip & 1) : 0;
         if (lane == 0) {
@@ -451,13 +417,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         uint8_t* s32 = stg + bsel * 4096;
         uint8_t* s16 = st32 ? stg + 4096 : stg + bsel * 4096;
         uint8_t* s16l = s16 + 2048;
-        if (st32) {
+        if (w32) {
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             *reinterpret_cast<float4*>(s32 + lane * 128 + ((q ^ (lane & 7)) << 4)) =
                 make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         }
-        if (st16) {
+        if (w16) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             __half2 h[4];
@@ -470,7 +436,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             u.w = *reinterpret_cast<uint32_t*>(&h[3]);
             const uint32_t off = lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4);
             *reinterpret_cast<uint4*>(s16 + off) = u;
-            if (st16lo) {
+            if (w16lo) {
               __half2 l[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -488,13 +454,129 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          const int s4 = p.ws ? split : 0;
-          if (st32) tma_store_5d(&tm.o32, s32, ocol0, sx, sy, sn, s4);
-          if (st16) tma_store_5d(&tm.o16, s16, ocol0, sx, sy, sn, 0);
-          if (st16lo) tma_store_5d(&tm.o16lo, s16l, ocol0, sx, sy, sn, 0);
+          if (raw_partial) {
+            tma_store_5d(&tm.ows, s32, ocol0, sx, sy, sn, split);
+          } else {
+            if (w32) tma_store_5d(&tm.o32, s32, ocol0, sx, sy, sn, 0);
+            if (w16) tma_store_5d(&tm.o16, s16, ocol0, sx, sy, sn, 0);
+            if (w16lo) tma_store_5d(&tm.o16lo, s16l, ocol0, sx, sy, sn, 0);
+          }
           tma_store_commit();
         }
+        if (!raw_partial && p.stats && w32) {
+          // GroupNorm statistics of the value just produced: lane c folds column c of the staged 32x32 tile
+          // (rows of one sample: rows_per_sample % 32 == 0 is checked on the host) into fp64 global accumulators
+          const uint32_t vmask = __ballot_sync(0xffffffffu, my_valid);
+          const int sample0 = __shfl_sync(0xffffffffu, my_sample, 0);
+          float cs = 0.f, cq = 0.f;
+#pragma unroll
+          for (int r = 0; r < 32; ++r) {
+            if ((vmask >> r) & 1u) {
+              float x = *reinterpret_cast<const float*>(s32 + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4) + (lane & 3) * 4);
+              cs += x;
+              cq = fmaf(x, x, cq);
+            }
+          }
+          if (vmask) {
+            double* dst = p.stats + (static_cast<size_t>(sample0) * p.N + ocol0 + lane) * 2;
+            atomicAdd(dst, static_cast<double>(cs));
+            atomicAdd(dst + 1, static_cast<double>(cq));
+          }
+        }
         ++flip;
+      };
+
+      const bool split_fast = p.ws && p.fast;
+#pragma unroll 1
+      for (int c = par; c < n_chunks; c += 2) {
+        float v[32];
+        int ocol0;
+        if (geglu) {
+          uint32_t xr[32], gr[32];
+          tmem_ld32(taddr + c * 32, xr);
+          tmem_ld32(taddr + HALF + c * 32, gr);
+          tmem_ld_wait();
+          const int colx = n_tile * BN + c * 32;  // accumulator column of the value half; gate at +HALF
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(xr[j]) * p.alpha;
+            float g = __uint_as_float(gr[j]) * p.alpha;
+            if (p.bias) {
+              x += __ldg(p.bias + colx + j);
+              g += __ldg(p.bias + colx + HALF + j);
+            }
+            v[j] = x * gelu_erf(g);
+          }
+          ocol0 = n_tile * HALF + c * 32;
+        } else {
+          uint32_t rr[32];
+          tmem_ld32(taddr + c * 32, rr);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
+          ocol0 = n_tile * BN + c * 32;
+        }
+        if (c == last_c) {  // accumulator fully read by this warp: hand the buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[ab]);
+        }
+        if (!p.fast) {
+          // scalar transposed path (row pitch not TMA-addressable); split-K partials are finished by
+          // splitk_epilogue_kernel on this path
+#pragma unroll
+          for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = v[j];
+          __syncwarp();
+          drain_chunk(p, stage, lane, my_row, my_sample, my_valid, ocol0, geglu ? p.N / 2 : p.N, geglu ? 2 : (p.ws ? 1 : 0),
+                      split);
+          __syncwarp();
+          continue;
+        }
+        emit(v, ocol0, !geglu && !split_fast, split_fast);
+      }
+      if (split_fast) {
+        // In-kernel split-K reduction: every CTA publishes its fp32 partial tile, takes a ticket for the output tile,
+        // and the last arriver sums all partials (L2-resident) and runs the fused epilogue. No second kernel.
+        if (lane == 0) {
+          tma_store_wait<0>();  // partial tile fully written
+          __threadfence();
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+        if (ew == 0 && lane == 0) {
+          const unsigned int old = atomicAdd(&p.tickets[n_tile * p.m_tiles + m_tile], 1u);
+          const bool last = old == static_cast<unsigned int>(p.splits - 1);
+          if (last) p.tickets[n_tile * p.m_tiles + m_tile] = 0;  // self-reset for the next launch
+          __threadfence();
+          *ticket_flag = last ? 1u : 0u;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+        const bool last = *ticket_flag != 0u;
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");  // flag consumed before the next tile rewrites it
+        if (last) {
+          const size_t plane = static_cast<size_t>(p.M) * p.N;
+#pragma unroll 1
+          for (int c = par; c < n_chunks; c += 2) {
+            const int ocol0 = n_tile * BN + c * 32;
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            if (my_valid) {
+              const float* src = p.ws + static_cast<size_t>(my_row) * p.N + ocol0;
+              for (int sp = 0; sp < p.splits; ++sp) {
+                const float4* s4 = reinterpret_cast<const float4*>(src + sp * plane);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  float4 t = __ldcg(s4 + q);
+                  v[4 * q] += t.x;
+                  v[4 * q + 1] += t.y;
+                  v[4 * q + 2] += t.z;
+                  v[4 * q + 3] += t.w;
+                }
+              }
+            }
+            emit(v, ocol0, true, false);
+          }
+        }
       }
     }
     if (lane == 0) tma_store_wait<0>();
@@ -745,6 +827,7 @@ extern "C" int sdb_gemm(const sdb_gemm_desc* d, sdb_stream_t stream) {
   tm.o32 = tm.b;
   tm.o16 = tm.b;
   tm.o16lo = tm.b;
+  tm.ows = tm.b;
   if (fast) {
     const uint32_t bnn = static_cast<uint32_t>(32 / (p.bw * p.bh));
     auto make_out = [&](CUtensorMap* m, const void* base, int elem, int ncols, long ld, int nsplit) -> int {
@@ -772,13 +855,30 @@ extern "C" int sdb_gemm(const sdb_gemm_desc* d, sdb_stream_t stream) {
       str[3] = pitch * M;
       return make_tmap(m, base, elem, elem == 4 ? 128 : 64, 5, dims, str, box);
     };
-    if (p.ws) {
-      if (make_out(&tm.o32, p.ws, 4, d->n, d->n, splits)) return 1;
-    } else {
-      if (p.out_f32 && make_out(&tm.o32, p.out_f32, 4, n_out, p.ldo, 1)) return 1;
-      if (p.out_f16 && make_out(&tm.o16, p.out_f16, 2, n_out, p.ldo, 1)) return 1;
-      if (p.out_f16_lo && make_out(&tm.o16lo, p.out_f16_lo, 2, n_out, p.ldo, 1)) return 1;
+    if (p.ws && make_out(&tm.ows, p.ws, 4, d->n, d->n, splits)) return 1;
+    if (p.out_f32 && make_out(&tm.o32, p.out_f32, 4, n_out, p.ldo, 1)) return 1;
+    if (p.out_f16 && make_out(&tm.o16, p.out_f16, 2, n_out, p.ldo, 1)) return 1;
+    if (p.out_f16_lo && make_out(&tm.o16lo, p.out_f16_lo, 2, n_out, p.ldo, 1)) return 1;
+  }
+  if (splits > 1 && fast) {
+    static unsigned int* tickets = nullptr;   // one counter per output tile; zeroed once, self-resetting in the kernel
+    constexpr size_t kTickets = 1 << 18;
+    if (!tickets) {
+      SDB_CUDA(cudaMalloc(&tickets, kTickets * sizeof(unsigned int)));
+      SDB_CUDA(cudaMemset(tickets, 0, kTickets * sizeof(unsigned int)));
     }
+    SDB_CHECK(static_cast<size_t>(p.m_tiles) * p.n_tiles <= kTickets, "sdb_gemm: too many split-K output tiles");
+    p.tickets = tickets;
+  }
+  // fused GroupNorm statistics: per-(sample, channel) sums of the fp32 output, accumulated by the epilogue
+  p.stats = nullptr;
+  if (d->stats_out) {
+    SDB_CHECK(fast && p.out_f32 && !geglu, "sdb_gemm: stats_out needs the TMA-store epilogue with an fp32 output");
+    SDB_CHECK(p.rows_per_sample % 32 == 0, "sdb_gemm: stats_out needs rows_per_sample %% 32 == 0 (got %d)",
+              p.rows_per_sample);
+    p.stats = static_cast<double*>(d->stats_out);
+    SDB_CUDA(cudaMemsetAsync(p.stats, 0, static_cast<size_t>((M + p.rows_per_sample - 1) / p.rows_per_sample) * d->n * 2 *
+                                             sizeof(double), st));
   }
 
   int rc;
@@ -790,7 +890,7 @@ extern "C" int sdb_gemm(const sdb_gemm_desc* d, sdb_stream_t stream) {
     default: rc = launch_gemm<256>(tm, p, st); break;
   }
   if (rc) return rc;
-  if (splits > 1) {
+  if (splits > 1 && !fast) {
     size_t total = static_cast<size_t>(p.M) * p.N;
     if (p.N % 4 == 0 && (p.ldo % 2 == 0)) {
       int blocks = static_cast<int>(std::min<size_t>((total / 4 + 255) / 256, static_cast<size_t>(sm_count()) * 8));

@@ -11,16 +11,23 @@ namespace sdb {
 constexpr int GN_THREADS = 256;
 constexpr int GN_MAX_CPT = 12;  // channels per thread: C <= 3072
 
-// pass 1: per (sample, group) sum / sum of squares.  grid = (slabs, nb). Thread t owns channel (t % cw) [+ k*cw] of
-// rows (t / cw) + k * (256 / cw): consecutive threads read consecutive channels (coalesced); per-channel partials are
-// combined in shared memory, reduced per group by one warp each, and added to the fp64 global accumulators.
+constexpr int GN_MAX_SLABS = 128;
+
+// pass 1: per (sample, group) mean / rstd. grid = (slabs, nb). Thread t owns channel (t % cw) [+ k*cw] of rows
+// (t / cw) + k * (256 / cw): consecutive threads read consecutive channels (coalesced), four rows in flight per
+// thread. Per-channel partials are combined in shared memory, reduced per group by one warp each and written as
+// per-block partials (no contended atomics); the last block of each sample (ticket counter) folds the partials in
+// fp64 and publishes mean / rstd.
 __global__ void __launch_bounds__(GN_THREADS)
     gn_stats_kernel(const float* __restrict__ x0, const float* __restrict__ x1, int c0, int c1, int hw, int groups,
-                    int rows_per_block, int cw, double* __restrict__ stats) {
+                    int rows_per_block, int cw, float eps, float* __restrict__ partial,
+                    unsigned int* __restrict__ counter, float* __restrict__ meanrstd) {
   extern __shared__ float gn_smem[];  // [2][C]
+  __shared__ bool is_last;
   const int C = c0 + c1;
   const int cpg = C / groups;
   const int n = blockIdx.y;
+  const int slabs = gridDim.x;
   const int r0 = blockIdx.x * rows_per_block;
   const int r1 = min(hw, r0 + rows_per_block);
   float* sum_s = gn_smem;
@@ -33,16 +40,24 @@ __global__ void __launch_bounds__(GN_THREADS)
   float s[GN_MAX_CPT], q[GN_MAX_CPT];
 #pragma unroll
   for (int j = 0; j < GN_MAX_CPT; ++j) s[j] = q[j] = 0.f;
-  for (int r = r0 + tr; r < r1; r += rstep) {
-    const float* p0 = x0 + (static_cast<size_t>(n) * hw + r) * c0;
-    const float* p1 = x1 ? x1 + (static_cast<size_t>(n) * hw + r) * c1 : nullptr;
+  const size_t base = static_cast<size_t>(n) * hw;
+  for (int r = r0 + tr; r < r1; r += 4 * rstep) {
 #pragma unroll
     for (int j = 0; j < GN_MAX_CPT; ++j) {
-      int c = tc + j * cw;
+      const int c = tc + j * cw;
       if (c < C) {
-        float v = c < c0 ? p0[c] : p1[c - c0];
-        s[j] += v;
-        q[j] += v * v;
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int rr = r + u * rstep;
+          v[u] = 0.f;
+          if (rr < r1) v[u] = c < c0 ? x0[(base + rr) * c0 + c] : x1[(base + rr) * c1 + (c - c0)];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          s[j] += v[u];
+          q[j] += v[u] * v[u];
+        }
       }
     }
   }
@@ -61,6 +76,7 @@ __global__ void __launch_bounds__(GN_THREADS)
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* my_part = partial + (static_cast<size_t>(n) * GN_MAX_SLABS + blockIdx.x) * groups * 2;
   for (int g = warp; g < groups; g += GN_THREADS / 32) {
     float a = 0.f, b = 0.f;
     for (int c = lane; c < cpg; c += 32) {
@@ -73,8 +89,35 @@ __global__ void __launch_bounds__(GN_THREADS)
       b += __shfl_xor_sync(0xffffffffu, b, o);
     }
     if (lane == 0) {
-      atomicAdd(&stats[(static_cast<size_t>(n) * groups + g) * 2], static_cast<double>(a));
-      atomicAdd(&stats[(static_cast<size_t>(n) * groups + g) * 2 + 1], static_cast<double>(b));
+      my_part[g * 2] = a;
+      my_part[g * 2 + 1] = b;
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(&counter[n], 1u) == static_cast<unsigned>(slabs - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const double cnt = static_cast<double>(hw) * cpg;
+  for (int g = warp; g < groups; g += GN_THREADS / 32) {
+    double a = 0.0, b = 0.0;
+    for (int sl = lane; sl < slabs; sl += 32) {
+      const float* pp = partial + ((static_cast<size_t>(n) * GN_MAX_SLABS + sl) * groups + g) * 2;
+      a += static_cast<double>(__ldcg(pp));
+      b += static_cast<double>(__ldcg(pp + 1));
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) {
+      double m = a / cnt;
+      double v = b / cnt - m * m;
+      if (v < 0) v = 0;
+      meanrstd[(static_cast<size_t>(n) * groups + g) * 2] = static_cast<float>(m);
+      meanrstd[(static_cast<size_t>(n) * groups + g) * 2 + 1] = static_cast<float>(1.0 / sqrt(v + static_cast<double>(eps)));
     }
   }
 }
@@ -82,26 +125,50 @@ __global__ void __launch_bounds__(GN_THREADS)
 // pass 2: normalise (+SiLU) -> fp16, optional raw fp16 cast. grid = (slabs, nb)
 __global__ void __launch_bounds__(GN_THREADS)
     gn_apply_kernel(const float* __restrict__ x0, const float* __restrict__ x1, int c0, int c1, int hw, int groups,
-                    int rows_per_block, const double* __restrict__ stats, const float* __restrict__ gamma,
+                    int rows_per_block, const float* __restrict__ meanrstd, const float* __restrict__ gamma,
                     const float* __restrict__ beta, float eps, int silu, __half* __restrict__ out,
-                    __half* __restrict__ raw, __half* __restrict__ out_lo, __half* __restrict__ raw_lo) {
+                    __half* __restrict__ raw, __half* __restrict__ out_lo, __half* __restrict__ raw_lo,
+                    const double* __restrict__ cs0, const double* __restrict__ cs1) {
   const int C = c0 + c1;
   const int cpg = C / groups;
   const int n = blockIdx.y;
   __shared__ float mean_s[64], rstd_s[64];
-  if (threadIdx.x < groups) {
-    double cnt = static_cast<double>(hw) * cpg;
-    double m = stats[(static_cast<size_t>(n) * groups + threadIdx.x) * 2] / cnt;
-    double v = stats[(static_cast<size_t>(n) * groups + threadIdx.x) * 2 + 1] / cnt - m * m;
-    if (v < 0) v = 0;
-    mean_s[threadIdx.x] = static_cast<float>(m);
-    rstd_s[threadIdx.x] = static_cast<float>(1.0 / sqrt(v + static_cast<double>(eps)));
+  if (cs0) {
+    // per-channel {sum, sum of squares} accumulated by the producing GEMM epilogues (sdb_gemm.stats_out): fold the
+    // channels of each group (8 lanes per group) in fp64
+    const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;
+    if (g < groups) {
+      double a = 0.0, b = 0.0;
+      for (int c = g * cpg + sub; c < (g + 1) * cpg; c += 8) {
+        const double* q = c < c0 ? cs0 + (static_cast<size_t>(n) * c0 + c) * 2
+                                 : cs1 + (static_cast<size_t>(n) * c1 + (c - c0)) * 2;
+        a += q[0];
+        b += q[1];
+      }
+#pragma unroll
+      for (int o = 4; o; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+      }
+      if (sub == 0) {
+        const double cnt = static_cast<double>(hw) * cpg;
+        double m = a / cnt;
+        double v = b / cnt - m * m;
+        if (v < 0) v = 0;
+        mean_s[g] = static_cast<float>(m);
+        rstd_s[g] = static_cast<float>(1.0 / sqrt(v + static_cast<double>(eps)));
+      }
+    }
+  } else if (threadIdx.x < groups) {
+    mean_s[threadIdx.x] = meanrstd[(static_cast<size_t>(n) * groups + threadIdx.x) * 2];
+    rstd_s[threadIdx.x] = meanrstd[(static_cast<size_t>(n) * groups + threadIdx.x) * 2 + 1];
   }
   __syncthreads();
   const int r0 = blockIdx.x * rows_per_block;
   const int r1 = min(hw, r0 + rows_per_block);
   const int c4 = C / 4;  // C is a multiple of 4 (checked on the host); c0 too
   const int total = (r1 - r0) * c4;
+#pragma unroll 4
   for (int i = threadIdx.x; i < total; i += blockDim.x) {
     int r = r0 + i / c4;
     int c = (i % c4) * 4;
@@ -221,7 +288,7 @@ using namespace sdb;
 extern "C" int sdb_groupnorm(const float* x0, const float* x1, int32_t c0, int32_t c1, int32_t nb, int32_t hw,
                              int32_t groups, const float* gamma, const float* beta, float eps, int32_t silu,
                              void* out_f16, void* raw_f16, void* out_lo_f16, void* raw_lo_f16, void* stats_ws,
-                             sdb_stream_t stream) {
+                             const void* chan_stats0, const void* chan_stats1, sdb_stream_t stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int C = c0 + c1;
   SDB_CHECK(x0 && out_f16 && stats_ws && gamma && beta, "sdb_groupnorm: null pointer");
@@ -229,33 +296,37 @@ extern "C" int sdb_groupnorm(const float* x0, const float* x1, int32_t c0, int32
   SDB_CHECK(groups > 0 && groups <= 64 && C % groups == 0, "sdb_groupnorm: C=%d not divisible by groups=%d", C, groups);
   SDB_CHECK(c0 % 4 == 0 && c1 % 4 == 0, "sdb_groupnorm: channel counts must be multiples of 4");
   SDB_CHECK(C <= GN_THREADS * GN_MAX_CPT, "sdb_groupnorm: C=%d too large", C);
-  size_t stats_bytes = static_cast<size_t>(nb) * groups * 2 * sizeof(double);
-  SDB_CUDA(cudaMemsetAsync(stats_ws, 0, stats_bytes, st));
+  // workspace layout: [nb][GN_MAX_SLABS][groups][2] float partials | [nb][groups][2] float mean/rstd | [nb] tickets
+  float* partial = static_cast<float*>(stats_ws);
+  float* meanrstd = partial + static_cast<size_t>(nb) * GN_MAX_SLABS * groups * 2;
+  unsigned int* counter = reinterpret_cast<unsigned int*>(meanrstd + static_cast<size_t>(nb) * groups * 2);
+  const bool fused_stats = chan_stats0 != nullptr && (c1 == 0 || chan_stats1 != nullptr) && groups <= 32;
+  if (!fused_stats) SDB_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int) * nb, st));
   SDB_CHECK(!raw_lo_f16 || raw_f16, "sdb_groupnorm: raw_lo needs raw");
   // channel-lane width: threads of a block cover cw channels x (256 / cw) rows at a time
   int cw = GN_THREADS;
   while (cw > 32 && cw / 2 >= C) cw /= 2;
   const int rstep = GN_THREADS / cw;
-  // one wave of blocks: every block ends with 2*groups fp64 atomics on the same few addresses, so more blocks only
-  // add contention (measured: 586 blocks -> 26 us, of which ~20 us atomics)
   int target_blocks = sm_count() * 4;
-  int stats_blocks = sm_count();
-  int slabs = std::max(1, std::min((hw + 4 * rstep - 1) / (4 * rstep), (stats_blocks + nb - 1) / nb));
+  int slabs = std::max(1, std::min(std::min((hw + rstep - 1) / rstep, GN_MAX_SLABS), (target_blocks + nb - 1) / nb));
   int rows_per_block = (hw + slabs - 1) / slabs;
   slabs = (hw + rows_per_block - 1) / rows_per_block;
   dim3 grid(slabs, nb);
-  gn_stats_kernel<<<grid, GN_THREADS, 2 * C * sizeof(float), st>>>(x0, x1, c0, c1, hw, groups, rows_per_block, cw,
-                                                                    static_cast<double*>(stats_ws));
-  SDB_LAUNCH_CHECK();
-  // apply: ~8 rows per block or more
-  int aslabs = std::max(1, std::min((hw + 7) / 8, (target_blocks + nb - 1) / nb));
+  if (!fused_stats) {
+    gn_stats_kernel<<<grid, GN_THREADS, 2 * C * sizeof(float), st>>>(x0, x1, c0, c1, hw, groups, rows_per_block, cw,
+                                                                      eps, partial, counter, meanrstd);
+    SDB_LAUNCH_CHECK();
+  }
+  // apply: enough blocks for a few waves, down to one row per block at small resolutions
+  int aslabs = std::max(1, std::min(hw, (target_blocks + nb - 1) / nb));
   int arows = (hw + aslabs - 1) / aslabs;
   aslabs = (hw + arows - 1) / arows;
   dim3 agrid(aslabs, nb);
-  gn_apply_kernel<<<agrid, GN_THREADS, 0, st>>>(x0, x1, c0, c1, hw, groups, arows,
-                                                static_cast<const double*>(stats_ws), gamma, beta, eps, silu,
+  gn_apply_kernel<<<agrid, GN_THREADS, 0, st>>>(x0, x1, c0, c1, hw, groups, arows, meanrstd, gamma, beta, eps, silu,
                                                 static_cast<__half*>(out_f16), static_cast<__half*>(raw_f16),
-                                                static_cast<__half*>(out_lo_f16), static_cast<__half*>(raw_lo_f16));
+                                                static_cast<__half*>(out_lo_f16), static_cast<__half*>(raw_lo_f16),
+                                                fused_stats ? static_cast<const double*>(chan_stats0) : nullptr,
+                                                static_cast<const double*>(chan_stats1));
   SDB_LAUNCH_CHECK();
   return 0;
 }

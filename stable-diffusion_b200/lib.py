@@ -37,6 +37,7 @@ class GemmDesc(C.Structure):
         ("splits", C.c_int32),
         ("workspace", C.c_void_p),
         ("workspace_floats", C.c_int64),
+        ("stats_out", C.c_void_p),
     ]
 
 
@@ -62,7 +63,7 @@ SIGNATURES = {
     "sdb_launch_count": ([], C.c_longlong),
     "sdb_gemm": ([C.POINTER(GemmDesc), _P], C.c_int),
     "sdb_attention": ([C.POINTER(AttnDesc), _P], C.c_int),
-    "sdb_groupnorm": ([_P, _P, _I, _I, _I, _I, _I, _P, _P, _F, _I, _P, _P, _P, _P, _P, _P], C.c_int),
+    "sdb_groupnorm": ([_P, _P, _I, _I, _I, _I, _I, _P, _P, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P], C.c_int),
     "sdb_layernorm": ([_P, _I, _I, _P, _P, _F, _P, _P, _P], C.c_int),
     "sdb_softmax_rows": ([_P, _I, _I, _F, _P, _P], C.c_int),
     "sdb_nchw_to_nhwc": ([_P, _I, _I, _I, _P, _P, _P], C.c_int),

@@ -52,12 +52,15 @@ def _chk32(t, name):
 
 def gemm(a0, b, *, a1=None, a2=None, a3=None, nb=None, h=None, w=None, taps=1, bias=None, film=None,
          rows_per_sample=0, residual=None, act=ACT_NONE, alpha=1.0, out_f16=None, out_f32=None, out_f16_lo=None,
-         want_f16=False, want_f32=False, want_lo=False, n=None, block_n=0, splits=0, workspace=None):
+         want_f16=False, want_f32=False, want_lo=False, n=None, block_n=0, splits=0, workspace=None,
+         want_stats=False):
     """acc = A @ B^T with fused epilogue (see sdb_gemm in include/sdb200.h).
 
     a0 (, a1, a2, a3): fp16 [..., c_i] NHWC activations or plain [rows, c_i] matrices, concatenated along K.
     b: fp16 [n, taps*sum(c_i)].
     Returns (out_f16, out_f32), or (out_f16, out_f32, out_f16_lo) when the hi/lo pair is requested.
+    want_stats: the epilogue also accumulates the GroupNorm statistics of the fp32 output; they are attached to the
+    output tensor (see channel_stats()) so the following groupnorm() skips its reduction pass.
     """
     _chk16(a0, "a0")
     _chk16(b, "b")
@@ -104,6 +107,13 @@ def gemm(a0, b, *, a1=None, a2=None, a3=None, nb=None, h=None, w=None, taps=1, b
     d.out_f16, d.out_f32, d.out_f16_lo = _ptr(out_f16), _ptr(out_f32), _ptr(out_f16_lo)
     d.ldo = 0
     d.block_n = block_n
+    stats = None
+    if want_stats and out_f32 is not None and act != ACT_GEGLU and (taps == 9 or rows_per_sample):
+        rps = rows_per_sample if rows_per_sample else h * w
+        if rps % 32 == 0 and n % 32 == 0 and M % rps == 0:
+            stats = torch.empty((M // rps, n, 2), dtype=torch.float64, device=a0.device)
+            d.stats_out = _ptr(stats)
+            out_f32._sdb_stats = stats   # travels with the tensor object (and, through ._base, with its views)
     d.splits = splits
     if splits and (splits > 1 or splits == -1):
         if workspace is None:
@@ -122,6 +132,14 @@ def gemm(a0, b, *, a1=None, a2=None, a3=None, nb=None, h=None, w=None, taps=1, b
     if out_f16_lo is not None:
         return out_f16, out_f32, out_f16_lo
     return out_f16, out_f32
+
+
+def channel_stats(x):
+    """Fused GroupNorm statistics attached to `x` (or the tensor it is a view of) by the gemm() that produced it."""
+    st = getattr(x, "_sdb_stats", None)
+    if st is None and x._base is not None and x._base.numel() == x.numel():
+        st = getattr(x._base, "_sdb_stats", None)
+    return st
 
 
 _WS = {}
@@ -175,10 +193,14 @@ def groupnorm(x0, gamma, beta, *, x1=None, groups=32, eps=1e-5, silu=False, want
     raw = torch.empty_like(out) if (want_raw or want_raw_lo) else None
     out_lo = torch.empty_like(out) if want_lo else None
     raw_lo = torch.empty_like(out) if want_raw_lo else None
-    ws = torch.empty(2 * nb * groups, dtype=torch.float64, device=x0.device)
+    ws = torch.empty(nb * (128 * groups * 2 + groups * 2 + 1), dtype=torch.float32, device=x0.device)
+    cs0 = channel_stats(x0)
+    cs1 = channel_stats(x1) if x1 is not None else None
+    if cs0 is None or (x1 is not None and cs1 is None):
+        cs0 = cs1 = None
     _l.check(_l.load().sdb_groupnorm(_ptr(x0), _ptr(x1), c0, c1, nb, h * w, groups, _ptr(gamma), _ptr(beta),
                                      eps, 1 if silu else 0, _ptr(out), _ptr(raw), _ptr(out_lo), _ptr(raw_lo), _ptr(ws),
-                                     _stream()), "sdb_groupnorm")
+                                     _ptr(cs0), _ptr(cs1), _stream()), "sdb_groupnorm")
     _count(3)
     if want_lo or want_raw_lo:
         return out, raw, out_lo, raw_lo

@@ -248,7 +248,7 @@ class UNetModel(nn.Module):
         else:
             hn, raw = ops.groupnorm(h, *r["gn1"], x1=skip, eps=1e-5, silu=True, want_raw="ws" in r)
         fv = film[:, r["film_off"]: r["film_off"] + r["cout"]]
-        _, h1 = ops.gemm(hn, r["w1"], taps=9, bias=r["b1"], film=fv, want_f32=True, splits=-1)
+        _, h1 = ops.gemm(hn, r["w1"], taps=9, bias=r["b1"], film=fv, want_f32=True, splits=-1, want_stats=True)
         h1 = h1.view(nb, H, Wd, r["cout"])
         hn2, _ = ops.groupnorm(h1, *r["gn2"], eps=1e-5, silu=True)
         if x3:    # skip 1x1 conv on the raw stream: [x_hi | x_lo | x_hi] . [W_hi | W_hi | W_lo]
@@ -258,7 +258,7 @@ class UNetModel(nn.Module):
         else:
             assert skip is None
             res = h.view(-1, r["cout"])
-        _, out = ops.gemm(hn2, r["w2"], taps=9, bias=r["b2"], residual=res, want_f32=True, splits=-1)
+        _, out = ops.gemm(hn2, r["w2"], taps=9, bias=r["b2"], residual=res, want_f32=True, splits=-1, want_stats=True)
         return out.view(nb, H, Wd, r["cout"])
 
     def _st(self, s, x, kv):
@@ -300,10 +300,11 @@ class UNetModel(nn.Module):
         if x3:
             t3, _, t3_lo = ops.gemm(g, s["w_ff2"], bias=s["b_ff2"], residual=t2, want_lo=True, splits=-1)
             _, out = ops.gemm(t3, s["w_out"], a1=t3_lo, a2=t3, bias=s["b_out"], residual=x.view(-1, ch), want_f32=True,
-                              splits=-1)
+                              splits=-1, rows_per_sample=ntok, want_stats=True)
         else:
             t3, _ = ops.gemm(g, s["w_ff2"], bias=s["b_ff2"], residual=t2, want_f16=True, splits=-1)
-            _, out = ops.gemm(t3, s["w_out"], bias=s["b_out"], residual=x.view(-1, ch), want_f32=True, splits=-1)
+            _, out = ops.gemm(t3, s["w_out"], bias=s["b_out"], residual=x.view(-1, ch), want_f32=True, splits=-1,
+                              rows_per_sample=ntok, want_stats=True)
         return out.view(nb, H, Wd, ch)
 
     def context_kv(self, context, static=False):
@@ -345,17 +346,18 @@ class UNetModel(nn.Module):
             elif kind == "down":
                 nb, H, Wd, c = h.shape
                 col = ops.im2col3x3(h, 2, 1, H // 2, Wd // 2, 9 * c)
-                _, o = ops.gemm(col, p["w"], bias=p["b"], want_f32=True, splits=-1)
+                _, o = ops.gemm(col, p["w"], bias=p["b"], want_f32=True, splits=-1,
+                                rows_per_sample=(H // 2) * (Wd // 2), want_stats=True)
                 h = o.view(nb, H // 2, Wd // 2, c)
             elif kind == "up":
                 nb, H, Wd, c = h.shape
                 up = ops.upsample2x(h)
-                _, o = ops.gemm(up, p["w"], taps=9, bias=p["b"], want_f32=True, splits=-1)
+                _, o = ops.gemm(up, p["w"], taps=9, bias=p["b"], want_f32=True, splits=-1, want_stats=True)
                 h = o.view(nb, 2 * H, 2 * Wd, c)
             elif kind == "conv_in":
                 nb, H, Wd, c = h.shape
                 col = ops.im2col3x3(h, 1, 1, H, Wd, 64)
-                _, o = ops.gemm(col, p["w"], bias=p["b"], want_f32=True)
+                _, o = ops.gemm(col, p["w"], bias=p["b"], want_f32=True, rows_per_sample=H * Wd, want_stats=True)
                 h = o.view(nb, H, Wd, p["cout"])
         return h
 

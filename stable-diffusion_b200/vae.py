@@ -151,10 +151,11 @@ class AutoencoderKL(nn.Module):
         if c["col"]:
             nb, H, Wd, _ = x32.shape
             col = ops.im2col3x3(x32, 1, 1, H, Wd, c["w"].shape[1])
-            _, o = ops.gemm(col, c["w"], bias=c["b"], want_f32=True, **epi)
+            _, o = ops.gemm(col, c["w"], bias=c["b"], want_f32=True, rows_per_sample=H * Wd, want_stats=True, **epi)
             return o.view(nb, H, Wd, c["cout"])
         nb, H, Wd, _ = x16.shape
-        _, o = ops.gemm(x16, c["w"], taps=9, bias=c["b"], want_f32=True, splits=-1, **epi)
+        # every conv output here feeds a GroupNorm next: let the epilogue accumulate its statistics
+        _, o = ops.gemm(x16, c["w"], taps=9, bias=c["b"], want_f32=True, splits=-1, want_stats=True, **epi)
         return o.view(nb, H, Wd, c["cout"])
 
     def _resnet(self, r, x):
@@ -192,7 +193,8 @@ class AutoencoderKL(nn.Module):
             if npad != n:
                 raise NotImplementedError("VAE attention needs h*w % 8 == 0")
             ops.gemm(p, vt.contiguous(), out_f16=o[b])
-        _, out = ops.gemm(o.view(-1, c), a["w_o"], bias=a["b_o"], residual=x.view(-1, c), want_f32=True)
+        _, out = ops.gemm(o.view(-1, c), a["w_o"], bias=a["b_o"], residual=x.view(-1, c), want_f32=True,
+                          rows_per_sample=n, want_stats=True)
         return out.view(nb, H, Wd, c)
 
     # ------------------------------------------------------------------ public API
@@ -231,7 +233,8 @@ class AutoencoderKL(nn.Module):
                 nb, H, Wd, c = h.shape
                 col = ops.im2col3x3(h, 2, 0, H // 2, Wd // 2, 9 * c)
                 rs = lvl["resample"]
-                _, o = ops.gemm(col, rs["w"], bias=rs["b"], want_f32=True, splits=-1)
+                _, o = ops.gemm(col, rs["w"], bias=rs["b"], want_f32=True, splits=-1,
+                                rows_per_sample=(H // 2) * (Wd // 2), want_stats=True)
                 h = o.view(nb, H // 2, Wd // 2, c)
         h = self._resnet(E["mid1"], h)
         h = self._attn(E["attn"], h)

@@ -274,3 +274,39 @@ def test_gemm_narrow_tiles_many_per_cta(S, cuda_dev):
         _, o32 = S.ops.gemm(a, b, want_f32=True, block_n=bn)
         ref = a.double() @ b.double().t()
         assert rel_l2(o32, ref) < 1e-5, (M, N, K, bn)
+
+
+def test_gemm_fused_groupnorm_stats_and_inkernel_splitk(S, cuda_dev):
+    """Epilogue-accumulated per-channel statistics feed groupnorm() without a reduction pass; split-K partials are
+    reduced by the last-arriving CTA inside the GEMM kernel."""
+    g = torch.Generator().manual_seed(31)
+    for (nb, h, w, c, n, splits) in [(2, 16, 16, 128, 320, 0), (2, 8, 8, 320, 640, 4), (3, 8, 8, 64, 64, -1), (2, 32, 32, 64, 128, 0)]:
+        x = _rand16((nb, h, w, c), cuda_dev, g)
+        wk = _rand16((n, 9 * c), cuda_dev, g, (9 * c) ** -0.5)
+        bias = torch.randn(n, generator=g).to(cuda_dev)
+        res = (torch.randn(nb * h * w, n, generator=g) * 2 + 0.7).to(cuda_dev)
+        _, o32 = S.ops.gemm(x, wk, taps=9, bias=bias, residual=res, want_f32=True, splits=splits, want_stats=True)
+        wt = wk.reshape(n, 3, 3, c).permute(0, 3, 1, 2).double()
+        ref = F.conv2d(x.double().permute(0, 3, 1, 2), wt, bias.double(), padding=1).permute(0, 2, 3, 1).reshape(-1, n) + res
+        assert rel_l2(o32, ref) < 1e-5, (nb, h, w, c, n, splits, rel_l2(o32, ref))
+        st = S.ops.channel_stats(o32)
+        assert st is not None and st.shape == (nb, n, 2)
+        r3 = ref.reshape(nb, h * w, n)
+        assert rel_l2(st[..., 0], r3.sum(1)) < 1e-5 and rel_l2(st[..., 1], (r3 * r3).sum(1)) < 1e-5
+        gamma = (1 + 0.1 * torch.randn(n, generator=g)).to(cuda_dev)
+        beta = (0.1 * torch.randn(n, generator=g)).to(cuda_dev)
+        y, _ = S.ops.groupnorm(o32.view(nb, h, w, n), gamma, beta, eps=1e-5, silu=True)   # uses the fused stats
+        yr = F.silu(F.group_norm(ref.float().reshape(nb, h, w, n).permute(0, 3, 1, 2), 32, gamma, beta, 1e-5)).permute(0, 2, 3, 1)
+        assert rel_l2(y.float(), yr) < 6e-4
+    # concat of two stat-carrying tensors (groups straddle the boundary: 192 + 64 channels, 8 per group)
+    xa = _rand16((2, 8, 8, 64), cuda_dev, g)
+    wa = _rand16((192, 9 * 64), cuda_dev, g, 0.05)
+    wb = _rand16((64, 9 * 64), cuda_dev, g, 0.05)
+    _, a32 = S.ops.gemm(xa, wa, taps=9, want_f32=True, want_stats=True)
+    _, b32 = S.ops.gemm(xa, wb, taps=9, want_f32=True, want_stats=True)
+    gam = torch.ones(256, device=cuda_dev)
+    bet = torch.zeros(256, device=cuda_dev)
+    y, _ = S.ops.groupnorm(a32.view(2, 8, 8, 192), gam, bet, x1=b32.view(2, 8, 8, 64), eps=1e-6)
+    cat = torch.cat([a32.view(2, 8, 8, 192), b32.view(2, 8, 8, 64)], -1)
+    yr = F.group_norm(cat.permute(0, 3, 1, 2), 32, gam, bet, 1e-6).permute(0, 2, 3, 1)
+    assert rel_l2(y.float(), yr) < 6e-4
