@@ -75,7 +75,7 @@ typedef struct sdb_gemm_desc {
                             bounded by workspace_floats); split-K needs workspace of splits*M*n floats */
   float* workspace;
   int64_t workspace_floats;
-  void* stats_out;       /* optional fp64 [M / rows_per_sample, n, 2]: per-(sample, channel) sum and sum of squares of
+  void* stats_out;       /* optional fp64 [4, M / rows_per_sample, n, 2] (4 accumulator copies, summed by the consumer): per-(sample, channel) sum and sum of squares of
                             the fp32 output, accumulated by the epilogue (zeroed by the call) — the GroupNorm statistics
                             of the tensor being produced, so no separate reduction pass reads it again */
 } sdb_gemm_desc;
@@ -118,7 +118,7 @@ int sdb_groupnorm(const float* x0, const float* x1, int32_t c0, int32_t c1, int3
                   void* out_lo_f16 /* optional low half of the normalised output (hi/lo split) */,
                   void* raw_lo_f16 /* optional low half of the raw cast */,
                   void* stats_ws /* scratch: nb * (128*groups*2 + groups*2 + 1) * 4 bytes */,
-                  const void* chan_stats0 /* optional fp64 [nb, c0, 2] from sdb_gemm.stats_out (skips the stats pass) */,
+                  const void* chan_stats0 /* optional fp64 [4, nb, c0, 2] from sdb_gemm.stats_out (skips the stats pass) */,
                   const void* chan_stats1 /* same for x1 */, sdb_stream_t stream);
 
 /* LayerNorm over the last dim of fp32 [rows, c] -> fp16 (attention.py:203-205, eps 1e-5). */

@@ -1,0 +1,126 @@
+#!/usr/bin/env python
+"""txt2img on the B200 engine with the reference script's flags (scripts/txt2img.py:98-235 of CompVis/stable-diffusion).
+
+  python scripts/txt2img.py --prompt "a photograph of an astronaut riding a horse" --plms --ckpt sd-v1-4.ckpt
+
+Without --ckpt the three stages get seeded random weights (no checkpoint ships offline); without the CLIP vocabulary
+files the prompt is replaced by seeded token ids (--token_seed). The safety checker and the invisible watermark of the
+reference script are third-party post-processing outside the denoising path and are not applied.
+"""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import sdb200  # noqa: E402
+from sdb200 import pipeline  # noqa: E402
+
+
+def load_model_from_config(ckpt, device, verbose=False):
+    """scripts/txt2img.py:49-66: torch.load(ckpt)["state_dict"] -> load_state_dict(strict=False) -> .cuda().eval()"""
+    model = pipeline.build_model()
+    if ckpt and os.path.exists(ckpt):
+        print(f"Loading model from {ckpt}")
+        pl_sd = torch.load(ckpt, map_location="cpu", weights_only=False)
+        if "global_step" in pl_sd:
+            print(f"Global Step: {pl_sd['global_step']}")
+        m, u = model.load_state_dict(pl_sd["state_dict"], strict=False)
+        if len(m) > 0 and verbose:
+            print("missing keys:", m)
+        if len(u) > 0 and verbose:
+            print("unexpected keys:", u)
+        model = model.to(device)
+    else:
+        print("no checkpoint given: seeded random-init weights (images will be noise-like)")
+        pipeline.load_random_weights(model, device, gen_device=device)
+    return model.eval()
+
+
+def synthetic_ids(n, seed, device):
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.randint(0, 49406, (n, 77), generator=g)
+    ids[:, 0] = 49406
+    ids[:, 20:] = 49407
+    return ids.to(device)
+
+
+def main():
+    p = argparse.ArgumentParser()
+    p.add_argument("--prompt", type=str, nargs="?", default="a painting of a virus monster playing guitar")
+    p.add_argument("--outdir", type=str, nargs="?", default="outputs/txt2img-samples")
+    p.add_argument("--skip_grid", action="store_true")
+    p.add_argument("--skip_save", action="store_true", help="do not save individual samples. For speed measurements.")
+    p.add_argument("--ddim_steps", type=int, default=50)
+    p.add_argument("--plms", action="store_true")
+    p.add_argument("--dpm_solver", action="store_true")
+    p.add_argument("--laion400m", action="store_true")
+    p.add_argument("--fixed_code", action="store_true")
+    p.add_argument("--ddim_eta", type=float, default=0.0)
+    p.add_argument("--n_iter", type=int, default=2)
+    p.add_argument("--H", type=int, default=512)
+    p.add_argument("--W", type=int, default=512)
+    p.add_argument("--C", type=int, default=4)
+    p.add_argument("--f", type=int, default=8)
+    p.add_argument("--n_samples", type=int, default=3)
+    p.add_argument("--n_rows", type=int, default=0)
+    p.add_argument("--scale", type=float, default=7.5)
+    p.add_argument("--from-file", type=str)
+    p.add_argument("--config", type=str, default="configs/stable-diffusion/v1-inference.yaml")
+    p.add_argument("--ckpt", type=str, default="models/ldm/stable-diffusion-v1/model.ckpt")
+    p.add_argument("--seed", type=int, default=42)
+    p.add_argument("--precision", type=str, choices=["full", "autocast"], default="autocast")
+    p.add_argument("--token_seed", type=int, default=1234, help="seed of the stand-in token ids (no tokenizer offline)")
+    opt = p.parse_args()
+    if opt.dpm_solver or opt.laion400m:
+        raise NotImplementedError("--dpm_solver / --laion400m are outside the SD-v1 PLMS/DDIM hot path of this engine")
+    torch.manual_seed(opt.seed)           # seed_everything (txt2img.py:243)
+    device = torch.device("cuda")
+    model = load_model_from_config(opt.ckpt, device)
+    pipe = pipeline.Txt2Img(model, sampler="plms" if opt.plms else "ddim", steps=opt.ddim_steps, scale=opt.scale,
+                            height=opt.H, width=opt.W, eta=opt.ddim_eta, f=opt.f, channels=opt.C)
+    os.makedirs(opt.outdir, exist_ok=True)
+    sample_path = os.path.join(opt.outdir, "samples")
+    os.makedirs(sample_path, exist_ok=True)
+    B = opt.n_samples
+    if opt.from_file:
+        with open(opt.from_file) as f:
+            prompts = f.read().splitlines()
+    else:
+        prompts = [opt.prompt]
+    enc = model.cond_stage_model
+    start_code = torch.randn([B, opt.C, opt.H // opt.f, opt.W // opt.f], device=device) if opt.fixed_code else None
+    base_count = len(os.listdir(sample_path))
+    tic = time.time()
+    n_img = 0
+    for n in range(opt.n_iter):
+        for pi, prompt in enumerate(prompts):
+            try:
+                ids = enc._tokenize(B * [prompt]).to(device)
+                un = enc._tokenize(B * [""]).to(device)
+            except RuntimeError as e:
+                if n == 0 and pi == 0:
+                    print(f"tokenizer unavailable ({e}); using seeded token ids")
+                ids = synthetic_ids(B, opt.token_seed + pi, device)
+                un = torch.full((B, 77), 49407, dtype=torch.long, device=device)
+                un[:, 0] = 49406
+            x_T = start_code if start_code is not None else torch.randn(
+                [B, opt.C, opt.H // opt.f, opt.W // opt.f], device=device)      # plms.py:124
+            img = pipe(ids, un if opt.scale != 1.0 else None, x_T=x_T)           # uint8 [B, H, W, 3]
+            n_img += B
+            if not opt.skip_save:
+                from PIL import Image
+                for x in img.cpu().numpy():
+                    Image.fromarray(x.astype(np.uint8)).save(os.path.join(sample_path, f"{base_count:05}.png"))
+                    base_count += 1
+    torch.cuda.synchronize()
+    toc = time.time()
+    print(f"Your samples are ready and waiting for you here: \n{opt.outdir} \n"
+          f"{n_img} images in {toc - tic:.2f} s ({n_img / (toc - tic):.2f} images/s). Enjoy.")
+
+
+if __name__ == "__main__":
+    main()

@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(192)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
   const int q0 = blockIdx.x * AQ;
   const int head = blockIdx.y;
   const int b = blockIdx.z;
@@ -88,6 +89,7 @@ __global__ void __launch_bounds__(192)
   tc_fence_after();
   const uint32_t tmem = tmem_base_smem;
 
+  pdl_wait();   // q / k / v come from the previous kernels; everything above overlapped their tail
   if (warp == 0) {
     if (elect_one()) {
       mbar_arrive_expect_tx(&q_full, Q_BYTES);
@@ -272,7 +274,7 @@ static int launch_attn(const CUtensorMap& q, const CUtensorMap& k, const CUtenso
     SDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured = true;
   }
-  kern<<<grid, 192, SMEM, st>>>(q, k, v, p);
+  SDB_CUDA(launch_pdl(kern, grid, dim3(192), SMEM, st, q, k, v, p));
   SDB_LAUNCH_CHECK();
   return 0;
 }

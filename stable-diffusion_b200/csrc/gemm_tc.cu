@@ -32,6 +32,7 @@ constexpr int EPI_WARPS = 8;
 constexpr int STG_WARP_BYTES = 8192;  // per epilogue warp: 2 x 4 KB fp32 tiles, or 2 x (2 KB hi + 2 KB lo) fp16 tiles
 constexpr int STAGING_BYTES = EPI_WARPS * STG_WARP_BYTES;
 constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
+constexpr int STAT_SLOTS = 4;   // fused GroupNorm statistics are spread over 4 accumulator copies (m_tile & 3)
 
 struct TmapPack {
   CUtensorMap a[MAX_SRC];
@@ -64,7 +65,8 @@ struct GemmArgs {
   float* ws;
   int act;
   double* stats;    // optional per-(sample, channel) {sum, sum of squares} of the fp32 output (GroupNorm statistics)
-  unsigned int* tickets;  // split-K: one arrival counter per output tile (self-resetting)
+  int stats_halves;       // 1: the 128 rows of a tile belong to one sample; 2: rows 0-63 / 64-127 to two samples
+  int n_samples;
   int fast;         // outputs go through the TMA-store epilogue
   int bw, bh;       // store box: bw x bh x (32 / (bw*bh)) output pixels per epilogue warp
 };
@@ -203,12 +205,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   __shared__ uint64_t acc_full[2];
   __shared__ uint64_t acc_empty[2];
   __shared__ uint32_t tmem_base_smem;
-  __shared__ uint32_t ticket_flag_smem;
-  uint32_t* ticket_flag = &ticket_flag_smem;
+  // fused GroupNorm statistics: [lane group][column][sum, sum of squares]; one writer per slot per tile and a
+  // fixed-order fold at the flush (deterministic; the cross-CTA combine uses fp64 atomics)
+  __shared__ float colsum[4 * BN * 2];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int tiles_total = p.m_tiles * p.n_tiles * p.splits;
+  pdl_launch_dependents();   // the next kernel may start its prologue while this one runs
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < p.nsrc; ++i) tma_prefetch_desc(&tm.a[i]);
@@ -241,6 +245,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   if (warp == 0) {
     if (elect_one()) {
       uint32_t i = 0;  // ring position, continues across tiles
+      // PDL: the weight (B) tiles do not depend on the previous kernel — start streaming them for the first ring
+      // pass of the first tile before waiting for the producer of the activations
+      int npre = 0;
+      if (blockIdx.x < tiles_total) {
+        const int rest0 = blockIdx.x / p.m_tiles;
+        const int n_tile0 = rest0 % p.n_tiles;
+        const int split0 = rest0 / p.n_tiles;
+        const int b0 = split0 * p.iters_per_split;
+        const int e0 = min(p.k_iters, b0 + p.iters_per_split);
+        npre = min(STAGES, e0 - b0);
+        for (int j = 0; j < npre; ++j) {
+          mbar_arrive_expect_tx(&full_bar[j], STAGE_BYTES);
+          tma_load_2d(smem + j * STAGE_BYTES + A_BYTES, &tm.b, &full_bar[j], (b0 + j) * BK, n_tile0 * BN);
+        }
+      }
+      pdl_wait();
       for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
         const int m_tile = tile % p.m_tiles;
         const int rest = tile / p.m_tiles;
@@ -262,8 +282,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         for (int it = it_begin; it < it_end; ++it, ++i) {
           const int s = i % STAGES;
           const uint32_t ph = (i / STAGES) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+          const bool prefetched = static_cast<int>(i) < npre;   // B already in flight, barrier already armed
+          if (!prefetched) {
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+          }
           const int tap = it / cpt;
           const int cc = it - tap * cpt;
           int dx = 0, dy = 0;
@@ -275,7 +298,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           while (src + 1 < p.nsrc && cc >= p.cb[src + 1]) ++src;
           uint8_t* a_s = smem + s * STAGE_BYTES;
           tma_load_4d(a_s, &tm.a[src], &full_bar[s], (cc - p.cb[src]) * BK, x0 + dx, y0 + dy, n0);
-          tma_load_2d(a_s + A_BYTES, &tm.b, &full_bar[s], it * BK, n_tile * BN);
+          if (!prefetched) tma_load_2d(a_s + A_BYTES, &tm.b, &full_bar[s], it * BK, n_tile * BN);
         }
       }
     }
@@ -311,6 +334,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     }
   } else {
     // epilogue warps 2..9 : TMEM lane group = warp % 4; the two warps of a lane group alternate chunks
+    pdl_wait();   // residual / FiLM reads and all output writes come after the previous kernel has completed
     const int ew = warp - 2;
     const int lg = warp & 3;
     const int par = ew >> 2;
@@ -464,10 +488,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           tma_store_commit();
         }
         if (!raw_partial && p.stats && w32) {
-          // GroupNorm statistics of the value just produced: lane c folds column c of the staged 32x32 tile
-          // (rows of one sample: rows_per_sample % 32 == 0 is checked on the host) into fp64 global accumulators
+          // GroupNorm statistics of the value just produced: lane c folds column c of the staged 32x32 tile into the
+          // CTA's shared column sums (flushed once per tile with one fp64 global atomic per column)
           const uint32_t vmask = __ballot_sync(0xffffffffu, my_valid);
-          const int sample0 = __shfl_sync(0xffffffffu, my_sample, 0);
           float cs = 0.f, cq = 0.f;
 #pragma unroll
           for (int r = 0; r < 32; ++r) {
@@ -477,16 +500,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
               cq = fmaf(x, x, cq);
             }
           }
-          if (vmask) {
-            double* dst = p.stats + (static_cast<size_t>(sample0) * p.N + ocol0 + lane) * 2;
-            atomicAdd(dst, static_cast<double>(cs));
-            atomicAdd(dst + 1, static_cast<double>(cq));
-          }
+          const int cl = ocol0 - n_tile * BN + lane;
+          colsum[(lg * BN + cl) * 2] = cs;
+          colsum[(lg * BN + cl) * 2 + 1] = cq;
         }
         ++flip;
       };
 
-      const bool split_fast = p.ws && p.fast;
+      const bool split_fast = p.ws && p.fast;   // raw fp32 partial planes; finished by splitk_epilogue_kernel
 #pragma unroll 1
       for (int c = par; c < n_chunks; c += 2) {
         float v[32];
@@ -534,49 +555,34 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         }
         emit(v, ocol0, !geglu && !split_fast, split_fast);
       }
-      if (split_fast) {
-        // In-kernel split-K reduction: every CTA publishes its fp32 partial tile, takes a ticket for the output tile,
-        // and the last arriver sums all partials (L2-resident) and runs the fused epilogue. No second kernel.
-        if (lane == 0) {
-          tma_store_wait<0>();  // partial tile fully written
-          __threadfence();
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
-        if (ew == 0 && lane == 0) {
-          const unsigned int old = atomicAdd(&p.tickets[n_tile * p.m_tiles + m_tile], 1u);
-          const bool last = old == static_cast<unsigned int>(p.splits - 1);
-          if (last) p.tickets[n_tile * p.m_tiles + m_tile] = 0;  // self-reset for the next launch
-          __threadfence();
-          *ticket_flag = last ? 1u : 0u;
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
-        const bool last = *ticket_flag != 0u;
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");  // flag consumed before the next tile rewrites it
-        if (last) {
-          const size_t plane = static_cast<size_t>(p.M) * p.N;
-#pragma unroll 1
-          for (int c = par; c < n_chunks; c += 2) {
-            const int ocol0 = n_tile * BN + c * 32;
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0.f;
-            if (my_valid) {
-              const float* src = p.ws + static_cast<size_t>(my_row) * p.N + ocol0;
-              for (int sp = 0; sp < p.splits; ++sp) {
-                const float4* s4 = reinterpret_cast<const float4*>(src + sp * plane);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                  float4 t = __ldcg(s4 + q);
-                  v[4 * q] += t.x;
-                  v[4 * q + 1] += t.y;
-                  v[4 * q + 2] += t.z;
-                  v[4 * q + 3] += t.w;
-                }
-              }
+      // ---- per-tile flush of the fused GroupNorm column sums (see emit)
+      if (p.stats && !p.ws) {
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");   // all smem column sums of this tile are in
+        const int et = threadIdx.x - 64;
+        const int halves = p.stats_halves;
+        for (int i = et; i < halves * BN; i += 32 * EPI_WARPS) {
+          const int hsel = i / BN, cl = i - hsel * BN;
+          const int col = n_tile * BN + cl;
+          const int r_probe = hsel * 64;   // first tile row of this half
+          int prow;
+          const bool pv = map_row(p, m_tile, r_probe, prow);
+          if (pv && col < p.N) {
+            const int sample = prow / p.rows_per_sample;
+            double* dst = p.stats + ((static_cast<size_t>(m_tile & (STAT_SLOTS - 1)) * p.n_samples + sample) * p.N + col) * 2;
+            float a, b;
+            if (halves == 2) {
+              a = colsum[((2 * hsel) * BN + cl) * 2] + colsum[((2 * hsel + 1) * BN + cl) * 2];
+              b = colsum[((2 * hsel) * BN + cl) * 2 + 1] + colsum[((2 * hsel + 1) * BN + cl) * 2 + 1];
+            } else {
+              a = (colsum[cl * 2] + colsum[(BN + cl) * 2]) + (colsum[(2 * BN + cl) * 2] + colsum[(3 * BN + cl) * 2]);
+              b = (colsum[cl * 2 + 1] + colsum[(BN + cl) * 2 + 1]) +
+                  (colsum[(2 * BN + cl) * 2 + 1] + colsum[(3 * BN + cl) * 2 + 1]);
             }
-            emit(v, ocol0, true, false);
+            atomicAdd(dst, static_cast<double>(a));
+            atomicAdd(dst + 1, static_cast<double>(b));
           }
         }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");   // slots consumed before the next tile rewrites them
       }
     }
     if (lane == 0) tma_store_wait<0>();
@@ -589,37 +595,104 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   }
 }
 
-// split-K second pass: sum partials and apply the fused epilogue (4 columns per thread when N % 4 == 0)
-template <int VEC>
+// split-K second pass: sum the fp32 partial planes and apply the fused epilogue. Block = 32 rows x 128 columns
+// (thread: 4 adjacent columns of rows ty, ty+8, ty+16, ty+24), so the GroupNorm column sums of the result fold
+// through shared memory into one fp64 atomic per column per block.
 __global__ void __launch_bounds__(256) splitk_epilogue_kernel(const GemmArgs p, int splits) {
-  const size_t total = static_cast<size_t>(p.M) * p.N;
-  const size_t nvec = total / VEC;
-  for (size_t v = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; v < nvec;
-       v += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const size_t idx = v * VEC;
-    const int row = static_cast<int>(idx / p.N);
-    const int col = static_cast<int>(idx - static_cast<size_t>(row) * p.N);
-    float acc[VEC];
+  __shared__ float red[8][128][2];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = blockIdx.x * 128 + tx * 4;
+  const size_t plane = static_cast<size_t>(p.M) * p.N;
+  float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
+  if (col < p.N) {
+    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias) bv = *reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
-    for (int s = 0; s < splits; ++s) {
-      const float* src = p.ws + static_cast<size_t>(s) * total + idx;
-      if (VEC == 4) {
-        float4 t = *reinterpret_cast<const float4*>(src);
-        acc[0] += t.x;
-        acc[1] += t.y;
-        acc[2] += t.z;
-        acc[3] += t.w;
-      } else {
-        acc[0] += src[0];
+    for (int i = 0; i < 4; ++i) {
+      const int row = blockIdx.y * 32 + ty + 8 * i;
+      if (row >= p.M) continue;
+      const float* src = p.ws + static_cast<size_t>(row) * p.N + col;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int sp = 0; sp < splits; ++sp) {
+        float4 t = __ldcg(reinterpret_cast<const float4*>(src + sp * plane));
+        acc.x += t.x;
+        acc.y += t.y;
+        acc.z += t.z;
+        acc.w += t.w;
+      }
+      float x[4] = {acc.x * p.alpha + bv.x, acc.y * p.alpha + bv.y, acc.z * p.alpha + bv.z, acc.w * p.alpha + bv.w};
+      const int sample = row / p.rows_per_sample;
+      if (p.film) {
+        float4 f = *reinterpret_cast<const float4*>(p.film + static_cast<size_t>(sample) * p.ldf + col);
+        x[0] += f.x; x[1] += f.y; x[2] += f.z; x[3] += f.w;
+      }
+      if (p.residual) {
+        float4 r = *reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(row) * p.ldr + col);
+        x[0] += r.x; x[1] += r.y; x[2] += r.z; x[3] += r.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        x[j] = apply_act(x[j], p.act);
+        cs[j] += x[j];
+        cq[j] = fmaf(x[j], x[j], cq[j]);
+      }
+      const size_t o = static_cast<size_t>(row) * p.ldo + col;
+      if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + o) = make_float4(x[0], x[1], x[2], x[3]);
+      if (p.out_f16) {
+        __half2 h0 = __floats2half2_rn(x[0], x[1]), h1 = __floats2half2_rn(x[2], x[3]);
+        uint2 u;
+        u.x = *reinterpret_cast<uint32_t*>(&h0);
+        u.y = *reinterpret_cast<uint32_t*>(&h1);
+        *reinterpret_cast<uint2*>(p.out_f16 + o) = u;
+        if (p.out_f16_lo) {
+          float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+          __half2 l0 = __floats2half2_rn(x[0] - f0.x, x[1] - f0.y), l1 = __floats2half2_rn(x[2] - f1.x, x[3] - f1.y);
+          uint2 w;
+          w.x = *reinterpret_cast<uint32_t*>(&l0);
+          w.y = *reinterpret_cast<uint32_t*>(&l1);
+          *reinterpret_cast<uint2*>(p.out_f16_lo + o) = w;
+        }
       }
     }
-    const int sample = row / p.rows_per_sample;
+  }
+  if (p.stats) {   // rows of one block belong to one sample (rows_per_sample % 32 == 0, checked on the host)
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      float x = acc[j] * p.alpha + (p.bias ? p.bias[col + j] : 0.f);
-      store_elem(p, x, row, sample, col + j, true);
+    for (int j = 0; j < 4; ++j) {
+      red[ty][tx * 4 + j][0] = cs[j];
+      red[ty][tx * 4 + j][1] = cq[j];
     }
+    __syncthreads();
+    if (threadIdx.x < 128) {
+      const int c = blockIdx.x * 128 + threadIdx.x;
+      if (c < p.N && blockIdx.y * 32 < p.M) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          a += red[k][threadIdx.x][0];
+          b += red[k][threadIdx.x][1];
+        }
+        const int sample = (blockIdx.y * 32) / p.rows_per_sample;
+        double* dst = p.stats + ((static_cast<size_t>(blockIdx.y & (STAT_SLOTS - 1)) * p.n_samples + sample) * p.N + c) * 2;
+        atomicAdd(dst, static_cast<double>(a));
+        atomicAdd(dst + 1, static_cast<double>(b));
+      }
+    }
+  }
+}
+
+// scalar variant for outputs whose width is not a multiple of 4 (no fused statistics)
+__global__ void __launch_bounds__(256) splitk_epilogue_scalar_kernel(const GemmArgs p, int splits) {
+  const size_t total = static_cast<size_t>(p.M) * p.N;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int row = static_cast<int>(idx / p.N);
+    const int col = static_cast<int>(idx - static_cast<size_t>(row) * p.N);
+    float acc = 0.f;
+    for (int sp = 0; sp < splits; ++sp) acc += p.ws[static_cast<size_t>(sp) * total + idx];
+    float x = acc * p.alpha + (p.bias ? p.bias[col] : 0.f);
+    store_elem(p, x, row, row / p.rows_per_sample, col, true);
   }
 }
 
@@ -634,7 +707,7 @@ static int launch_gemm(const TmapPack& tm, const GemmArgs& p, cudaStream_t st) {
   }
   const int tiles = p.m_tiles * p.n_tiles * p.splits;
   const int grid = std::min(tiles, sm_count());
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM, st>>>(tm, p);
+  SDB_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM, st, tm, p));
   SDB_LAUNCH_CHECK();
   return 0;
 }
@@ -860,25 +933,17 @@ extern "C" int sdb_gemm(const sdb_gemm_desc* d, sdb_stream_t stream) {
     if (p.out_f16 && make_out(&tm.o16, p.out_f16, 2, n_out, p.ldo, 1)) return 1;
     if (p.out_f16_lo && make_out(&tm.o16lo, p.out_f16_lo, 2, n_out, p.ldo, 1)) return 1;
   }
-  if (splits > 1 && fast) {
-    static unsigned int* tickets = nullptr;   // one counter per output tile; zeroed once, self-resetting in the kernel
-    constexpr size_t kTickets = 1 << 18;
-    if (!tickets) {
-      SDB_CUDA(cudaMalloc(&tickets, kTickets * sizeof(unsigned int)));
-      SDB_CUDA(cudaMemset(tickets, 0, kTickets * sizeof(unsigned int)));
-    }
-    SDB_CHECK(static_cast<size_t>(p.m_tiles) * p.n_tiles <= kTickets, "sdb_gemm: too many split-K output tiles");
-    p.tickets = tickets;
-  }
   // fused GroupNorm statistics: per-(sample, channel) sums of the fp32 output, accumulated by the epilogue
   p.stats = nullptr;
+  p.stats_halves = 1;
+  p.n_samples = static_cast<int>((M + p.rows_per_sample - 1) / p.rows_per_sample);
   if (d->stats_out) {
     SDB_CHECK(fast && p.out_f32 && !geglu, "sdb_gemm: stats_out needs the TMA-store epilogue with an fp32 output");
-    SDB_CHECK(p.rows_per_sample % 32 == 0, "sdb_gemm: stats_out needs rows_per_sample %% 32 == 0 (got %d)",
+    SDB_CHECK(p.rows_per_sample % 64 == 0, "sdb_gemm: stats_out needs rows_per_sample %% 64 == 0 (got %d)",
               p.rows_per_sample);
     p.stats = static_cast<double*>(d->stats_out);
-    SDB_CUDA(cudaMemsetAsync(p.stats, 0, static_cast<size_t>((M + p.rows_per_sample - 1) / p.rows_per_sample) * d->n * 2 *
-                                             sizeof(double), st));
+    p.stats_halves = (p.rows_per_sample % 128 == 0) ? 1 : 2;
+    SDB_CUDA(cudaMemsetAsync(p.stats, 0, static_cast<size_t>(STAT_SLOTS) * p.n_samples * d->n * 2 * sizeof(double), st));
   }
 
   int rc;
@@ -890,14 +955,16 @@ extern "C" int sdb_gemm(const sdb_gemm_desc* d, sdb_stream_t stream) {
     default: rc = launch_gemm<256>(tm, p, st); break;
   }
   if (rc) return rc;
-  if (splits > 1 && !fast) {
-    size_t total = static_cast<size_t>(p.M) * p.N;
-    if (p.N % 4 == 0 && (p.ldo % 2 == 0)) {
-      int blocks = static_cast<int>(std::min<size_t>((total / 4 + 255) / 256, static_cast<size_t>(sm_count()) * 8));
-      splitk_epilogue_kernel<4><<<blocks, 256, 0, st>>>(p, splits);
+  if (splits > 1) {
+    const bool vec = (p.N % 4 == 0) && (p.ldo % 4 == 0) && (!p.residual || p.ldr % 4 == 0) && (!p.film || p.ldf % 4 == 0);
+    if (vec) {
+      dim3 grid((p.N + 127) / 128, (p.M + 31) / 32);
+      SDB_CUDA(launch_pdl(splitk_epilogue_kernel, grid, dim3(256), 0, st, p, splits));
     } else {
+      SDB_CHECK(!p.stats, "sdb_gemm: stats_out with split-K needs n %% 4 == 0");
+      size_t total = static_cast<size_t>(p.M) * p.N;
       int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(sm_count()) * 8));
-      splitk_epilogue_kernel<1><<<blocks, 256, 0, st>>>(p, splits);
+      splitk_epilogue_scalar_kernel<<<blocks, 256, 0, st>>>(p, splits);
     }
     SDB_LAUNCH_CHECK();
   }

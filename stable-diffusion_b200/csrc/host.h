@@ -41,6 +41,26 @@ int sm_count();
 void count_launch();
 long long launch_count();
 
+// Launch with the programmatic-stream-serialization attribute (PDL): the kernel may begin while its predecessor in the
+// stream drains; it must execute griddepcontrol.wait before touching memory the predecessor produces.
+// SDB_PDL=0 in the environment disables the attribute (plain stream order).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 #define SDB_LAUNCH_CHECK()              \
   do {                                  \
     ::sdb::count_launch();              \

@@ -4,6 +4,7 @@
 // ldm/modules/attention.py:76-77 (Normalize, eps 1e-6), :203-205 (LayerNorm), ldm/modules/diffusionmodules/model.py:38-39.
 #include "../../include/sdb200.h"
 #include "host.h"
+#include "ptx.cuh"
 #include <cuda_fp16.h>
 
 namespace sdb {
@@ -133,6 +134,8 @@ __global__ void __launch_bounds__(GN_THREADS)
   const int cpg = C / groups;
   const int n = blockIdx.y;
   __shared__ float mean_s[64], rstd_s[64];
+  pdl_launch_dependents();
+  pdl_wait();
   if (cs0) {
     // per-channel {sum, sum of squares} accumulated by the producing GEMM epilogues (sdb_gemm.stats_out): fold the
     // channels of each group (8 lanes per group) in fp64
@@ -140,10 +143,14 @@ __global__ void __launch_bounds__(GN_THREADS)
     if (g < groups) {
       double a = 0.0, b = 0.0;
       for (int c = g * cpg + sub; c < (g + 1) * cpg; c += 8) {
-        const double* q = c < c0 ? cs0 + (static_cast<size_t>(n) * c0 + c) * 2
-                                 : cs1 + (static_cast<size_t>(n) * c1 + (c - c0)) * 2;
-        a += q[0];
-        b += q[1];
+        // the producers spread their atomics over 4 accumulator copies [slot][nb][c][2]
+#pragma unroll
+        for (int slot = 0; slot < 4; ++slot) {
+          const double* q = c < c0 ? cs0 + ((static_cast<size_t>(slot) * gridDim.y + n) * c0 + c) * 2
+                                   : cs1 + ((static_cast<size_t>(slot) * gridDim.y + n) * c1 + (c - c0)) * 2;
+          a += q[0];
+          b += q[1];
+        }
       }
 #pragma unroll
       for (int o = 4; o; o >>= 1) {
@@ -222,6 +229,8 @@ __global__ void __launch_bounds__(256)
                      const float* __restrict__ beta, float eps, __half* __restrict__ out, float* __restrict__ out32) {
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  pdl_wait();
   if (warp >= rows) return;
   const float* p = x + static_cast<size_t>(warp) * C;
   float v[NPL];
@@ -322,11 +331,12 @@ extern "C" int sdb_groupnorm(const float* x0, const float* x1, int32_t c0, int32
   int arows = (hw + aslabs - 1) / aslabs;
   aslabs = (hw + arows - 1) / arows;
   dim3 agrid(aslabs, nb);
-  gn_apply_kernel<<<agrid, GN_THREADS, 0, st>>>(x0, x1, c0, c1, hw, groups, arows, meanrstd, gamma, beta, eps, silu,
-                                                static_cast<__half*>(out_f16), static_cast<__half*>(raw_f16),
-                                                static_cast<__half*>(out_lo_f16), static_cast<__half*>(raw_lo_f16),
-                                                fused_stats ? static_cast<const double*>(chan_stats0) : nullptr,
-                                                static_cast<const double*>(chan_stats1));
+  SDB_CUDA(launch_pdl(gn_apply_kernel, agrid, dim3(GN_THREADS), 0, st, x0, x1, c0, c1, hw, groups, arows,
+                      static_cast<const float*>(meanrstd), gamma, beta, eps, silu, static_cast<__half*>(out_f16),
+                      static_cast<__half*>(raw_f16), static_cast<__half*>(out_lo_f16),
+                      static_cast<__half*>(raw_lo_f16),
+                      fused_stats ? static_cast<const double*>(chan_stats0) : static_cast<const double*>(nullptr),
+                      static_cast<const double*>(chan_stats1)));
   SDB_LAUNCH_CHECK();
   return 0;
 }
@@ -340,7 +350,7 @@ extern "C" int sdb_layernorm(const float* x, int32_t rows, int32_t c, const floa
   int blocks = (rows + warps_per_block - 1) / warps_per_block;
   __half* o16 = static_cast<__half*>(out_f16);
   const int npl = (c + 31) / 32;
-#define SDB_LN(N) layernorm_kernel<N><<<blocks, warps_per_block * 32, 0, st>>>(x, rows, c, gamma, beta, eps, o16, out_f32)
+#define SDB_LN(N) SDB_CUDA(launch_pdl(layernorm_kernel<N>, dim3(blocks), dim3(warps_per_block * 32), 0, st, x, rows, c, gamma, beta, eps, o16, out_f32))
   if (npl <= 2) SDB_LN(2);
   else if (npl <= 4) SDB_LN(4);
   else if (npl <= 10) SDB_LN(10);

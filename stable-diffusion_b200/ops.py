@@ -110,8 +110,8 @@ def gemm(a0, b, *, a1=None, a2=None, a3=None, nb=None, h=None, w=None, taps=1, b
     stats = None
     if want_stats and out_f32 is not None and act != ACT_GEGLU and (taps == 9 or rows_per_sample):
         rps = rows_per_sample if rows_per_sample else h * w
-        if rps % 32 == 0 and n % 32 == 0 and M % rps == 0:
-            stats = torch.empty((M // rps, n, 2), dtype=torch.float64, device=a0.device)
+        if rps % 64 == 0 and n % 32 == 0 and M % rps == 0:
+            stats = torch.empty((4, M // rps, n, 2), dtype=torch.float64, device=a0.device)
             d.stats_out = _ptr(stats)
             out_f32._sdb_stats = stats   # travels with the tensor object (and, through ._base, with its views)
     d.splits = splits

@@ -290,7 +290,8 @@ def test_gemm_fused_groupnorm_stats_and_inkernel_splitk(S, cuda_dev):
         ref = F.conv2d(x.double().permute(0, 3, 1, 2), wt, bias.double(), padding=1).permute(0, 2, 3, 1).reshape(-1, n) + res
         assert rel_l2(o32, ref) < 1e-5, (nb, h, w, c, n, splits, rel_l2(o32, ref))
         st = S.ops.channel_stats(o32)
-        assert st is not None and st.shape == (nb, n, 2)
+        assert st is not None and st.shape == (4, nb, n, 2)
+        st = st.sum(0)
         r3 = ref.reshape(nb, h * w, n)
         assert rel_l2(st[..., 0], r3.sum(1)) < 1e-5 and rel_l2(st[..., 1], (r3 * r3).sum(1)) < 1e-5
         gamma = (1 + 0.1 * torch.randn(n, generator=g)).to(cuda_dev)
