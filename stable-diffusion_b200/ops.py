@@ -16,6 +16,7 @@ from .lib import ACT_GEGLU, ACT_NONE, ACT_QUICK_GELU, ACT_SILU, AttnDesc, GemmDe
 LAUNCHES = 0        # op calls made through this module
 _GRAPH_LAUNCHES = 0  # kernels replayed from CUDA graphs (counted at capture time, added per replay)
 PROFILE = None      # when a list: gemm()/attention() append (kind, flops, start_event, end_event)
+RECORD = None       # when a list: gemm() appends (desc, algorithmic_flops, keepalive) so bench.py can replay the launches
 
 
 def launch_count():
@@ -121,6 +122,10 @@ def gemm(a0, b, *, a1=None, a2=None, a3=None, nb=None, h=None, w=None, taps=1, b
         assert splits == -1 or workspace.numel() >= splits * M * n
         d.workspace = _ptr(workspace)
         d.workspace_floats = workspace.numel()
+    if RECORD is not None:
+        # operand-split passes ([A_hi|A_lo|A_hi]) are overhead, not algorithmic work: count K once
+        k_alg = b.shape[1] // 3 if (len(srcs) == 3 and srcs[0] is srcs[2]) else b.shape[1]
+        RECORD.append((d, 2.0 * M * n * k_alg, (srcs, b, bias, film, residual, out_f16, out_f32, out_f16_lo, workspace)))
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
