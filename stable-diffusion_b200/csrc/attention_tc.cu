@@ -16,6 +16,14 @@ namespace sdb {
 
 constexpr int AQ = 128;   // query rows per CTA
 constexpr int AKV = 64;   // kv rows per iteration
+// K / V^T ring depth. The next K tile can only be requested once the PV MMA that last read the slot has finished, so
+// with 2 slots the ~1 us TMA round trip sat on the per-iteration critical path (155 us for N=4096, d=40); 3 slots take
+// it off (DPAD 192 keeps 2: shared memory).
+template <int DPAD>
+struct AttnCfg {
+  static constexpr int ST = DPAD <= 128 ? 3 : 2;
+  static constexpr int SMEM = AQ * DPAD * 2 + ST * (2 * AKV * DPAD * 2) + 2 * AQ * AKV * 2 + 1024;
+};
 
 struct AttnArgs {
   int nq, nkv, d, heads;
@@ -42,17 +50,18 @@ __global__ void __launch_bounds__(192)
   constexpr int V_BYTES = DPAD * AKV * 2;
   constexpr int P_BYTES = AQ * AKV * 2;
   constexpr int TMEM_COLS = (128 + DPAD) <= 256 ? 256 : 512;
+  constexpr int ST = AttnCfg<DPAD>::ST;
   constexpr uint32_t O_COL = 128;
 
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment by offset (keeps the shared address space visible to the compiler: STS, not generic ST)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* q_s = smem;
-  uint8_t* k_s = q_s + Q_BYTES;        // 2 stages
-  uint8_t* v_s = k_s + 2 * K_BYTES;    // 2 stages
-  uint8_t* p_s = v_s + 2 * V_BYTES;    // 2 buffers
+  uint8_t* k_s = q_s + Q_BYTES;        // ST stages
+  uint8_t* v_s = k_s + ST * K_BYTES;   // ST stages
+  uint8_t* p_s = v_s + ST * V_BYTES;   // 2 buffers
 
-  __shared__ uint64_t q_full, k_full[2], v_full[2], kv_empty[2], s_full[2], p_full[2], pv_done[2];
+  __shared__ uint64_t q_full, k_full[ST], v_full[ST], kv_empty[ST], s_full[2], p_full[2], pv_done[2];
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5;
@@ -70,10 +79,12 @@ __global__ void __launch_bounds__(192)
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     mbar_init(&q_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < ST; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&v_full[i], 1);
       mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 128);
       mbar_init(&pv_done[i], 1);
@@ -96,8 +107,8 @@ __global__ void __launch_bounds__(192)
       for (int pn = 0; pn < PANELS; ++pn)
         tma_load_3d(q_s + pn * (AQ * 128), &tmQ, &q_full, head * DPAD + pn * 64, q0, b);
       for (int j = 0; j < n_iter; ++j) {
-        int s = j & 1;
-        uint32_t ph = (j >> 1) & 1;
+        int s = j % ST;
+        uint32_t ph = (j / ST) & 1;
         mbar_wait(&kv_empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&k_full[s], K_BYTES);
         for (int pn = 0; pn < PANELS; ++pn)
@@ -112,10 +123,11 @@ __global__ void __launch_bounds__(192)
       constexpr uint32_t idesc_o = umma_idesc_f16(AQ, DPAD);
       const uint32_t q_addr = smem_u32(q_s);
       auto issue_s = [&](int j) {
-        int s = j & 1;
-        mbar_wait(&k_full[s], (j >> 1) & 1);
+        const int s = j & 1;            // S accumulator buffer
+        const int ks = j % ST;          // K/V ring slot
+        mbar_wait(&k_full[ks], (j / ST) & 1);
         tc_fence_after();
-        const uint32_t k_addr = smem_u32(k_s + s * K_BYTES);
+        const uint32_t k_addr = smem_u32(k_s + ks * K_BYTES);
 #pragma unroll
         for (int kk = 0; kk < DPAD / 16; ++kk) {
           uint64_t da = umma_desc_k128(q_addr + (kk >> 2) * (AQ * 128) + (kk & 3) * 32);
@@ -130,18 +142,19 @@ __global__ void __launch_bounds__(192)
         int s = j & 1;
         uint32_t ph = (j >> 1) & 1;
         if (j + 1 < n_iter) issue_s(j + 1);
+        const int ks = j % ST;
         mbar_wait(&p_full[s], ph);
-        mbar_wait(&v_full[s], ph);
+        mbar_wait(&v_full[ks], (j / ST) & 1);
         tc_fence_after();
         const uint32_t p_addr = smem_u32(p_s + s * P_BYTES);
-        const uint32_t v_addr = smem_u32(v_s + s * V_BYTES);
+        const uint32_t v_addr = smem_u32(v_s + ks * V_BYTES);
 #pragma unroll
         for (int kk = 0; kk < AKV / 16; ++kk) {
           uint64_t da = umma_desc_k128(p_addr + kk * 32);
           uint64_t db = umma_desc_k128(v_addr + kk * 32);
           umma_f16(tmem + O_COL, da, db, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
         }
-        umma_commit(&kv_empty[s]);
+        umma_commit(&kv_empty[ks]);
         umma_commit(&pv_done[s]);
       }
     }
@@ -267,7 +280,7 @@ __global__ void __launch_bounds__(192)
 template <int DPAD>
 static int launch_attn(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnArgs& p, dim3 grid,
                        cudaStream_t st) {
-  constexpr int SMEM = DPAD * 768 + 2 * AQ * AKV * 2 + 1024;
+  constexpr int SMEM = AttnCfg<DPAD>::SMEM;
   auto kern = attention_tc_kernel<DPAD>;
   static bool configured = false;
   if (!configured) {

@@ -58,12 +58,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU box.
+// Bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU box. The poll loop is kept to
+// try_wait + counter (the hardware suspends the thread inside try_wait): waiting warps must not eat the issue slots of
+// the compute warps that share their scheduler.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
+    if (++spins == (1u << 24)) {
       printf("sdb: mbarrier wait timeout block(%d,%d,%d) thread %d bar@%u parity %u\n", blockIdx.x, blockIdx.y,
              blockIdx.z, threadIdx.x, smem_u32(bar), parity);
       __trap();

@@ -17,6 +17,8 @@ LAUNCHES = 0        # op calls made through this module
 _GRAPH_LAUNCHES = 0  # kernels replayed from CUDA graphs (counted at capture time, added per replay)
 PROFILE = None      # when a list: gemm()/attention() append (kind, flops, start_event, end_event)
 RECORD = None       # when a list: gemm() appends (desc, algorithmic_flops, keepalive) so bench.py can replay the launches
+AUTOTUNE = False    # when True, gemm() times the (block_n, split-K) candidates of an unseen problem once and caches the best
+TUNED = {}          # problem key -> (block_n, splits)
 
 
 def launch_count():
@@ -122,6 +124,14 @@ def gemm(a0, b, *, a1=None, a2=None, a3=None, nb=None, h=None, w=None, taps=1, b
         assert splits == -1 or workspace.numel() >= splits * M * n
         d.workspace = _ptr(workspace)
         d.workspace_floats = workspace.numel()
+    if block_n == 0 and splits in (0, -1) and act != ACT_GEGLU:
+        key = (M, n, b.shape[1], taps, len(srcs), bias is not None, film is not None, residual is not None, act,
+               out_f16 is not None, out_f32 is not None, out_f16_lo is not None, stats is not None)
+        choice = TUNED.get(key)
+        if choice is None and AUTOTUNE:
+            choice = TUNED[key] = _tune_gemm(d, M, n, b.shape[1] // 64)
+        if choice is not None:
+            d.block_n, d.splits = choice
     if RECORD is not None:
         # operand-split passes ([A_hi|A_lo|A_hi]) are overhead, not algorithmic work: count K once
         k_alg = b.shape[1] // 3 if (len(srcs) == 3 and srcs[0] is srcs[2]) else b.shape[1]
@@ -145,6 +155,43 @@ def channel_stats(x):
     if st is None and x._base is not None and x._base.numel() == x.numel():
         st = getattr(x._base, "_sdb_stats", None)
     return st
+
+
+def _tune_gemm(d, M, n, k_iters):
+    """Time the tile-width / split-K candidates of one GEMM problem on its real operands (CUDA events, GPU kept busy by
+    a leading spin so host launch gaps do not enter) and return the fastest (block_n, splits)."""
+    lib = _l.load()
+    st = _stream()
+    cands = []
+    for bn in (64, 128, 160, 256):
+        pad = (n + bn - 1) // bn * bn - n
+        if bn > 64 and pad >= bn // 2:
+            continue
+        for sp in (1, 2, 3, 4, 6, 8, 12, 16, 24, 32):
+            if sp > 1 and (k_iters // sp < 2 or sp * M * n > d.workspace_floats):
+                continue
+            tiles = ((M + 127) // 128) * ((n + bn - 1) // bn) * sp
+            if sp > 1 and tiles > 3 * 148:
+                continue
+            cands.append((bn, sp))
+    best, best_t = (0, -1), float("inf")
+    keep = (d.block_n, d.splits)
+    for bn, sp in cands:
+        d.block_n, d.splits = bn, sp
+        if lib.sdb_gemm(C.byref(d), st) != 0:      # warm-up / validity
+            continue
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda._sleep(400_000)
+        e0.record()
+        for _ in range(4):
+            lib.sdb_gemm(C.byref(d), st)
+        e1.record()
+        e1.synchronize()
+        t = e0.elapsed_time(e1)
+        if t < best_t:
+            best, best_t = (bn, sp), t
+    d.block_n, d.splits = keep
+    return best
 
 
 _WS = {}

@@ -113,6 +113,7 @@ class UNetModel(nn.Module):
         self._kv_static = {}
         self._graphs = {}
         self.use_cuda_graph = False   # replay one captured graph per UNet evaluation (set by the pipeline / bench)
+        self.autotune = True          # graph mode: pick (block_n, split-K) per GEMM problem by measurement before capture
 
     # ------------------------------------------------------------------ weights
     def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
@@ -393,7 +394,12 @@ class UNetModel(nn.Module):
             st = torch.zeros((shape[0],), dtype=torch.float32, device=dev)
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):      # warm-up outside capture: cudaFuncSetAttribute, allocator pools
+            with torch.cuda.stream(side):      # warm-up outside capture: cudaFuncSetAttribute, allocator pools,
+                ops.AUTOTUNE = self.autotune   # and one-time (block_n, split-K) selection per GEMM problem
+                try:
+                    self._forward_impl(sx, st, kvs)
+                finally:
+                    ops.AUTOTUNE = False
                 self._forward_impl(sx, st, kvs)
             torch.cuda.current_stream().wait_stream(side)
             graph = torch.cuda.CUDAGraph()
