@@ -78,6 +78,7 @@ typedef struct sdb_gemm_desc {
   void* stats_out;       /* optional fp64 [4, M / rows_per_sample, n, 2] (4 accumulator copies, summed by the consumer): per-(sample, channel) sum and sum of squares of
                             the fp32 output, accumulated by the epilogue (zeroed by the call) — the GroupNorm statistics
                             of the tensor being produced, so no separate reduction pass reads it again */
+  int32_t stats_prezeroed; /* non-zero: the caller already zeroed stats_out (one arena memset per forward pass) */
 } sdb_gemm_desc;
 
 int sdb_gemm(const sdb_gemm_desc* d, sdb_stream_t stream);

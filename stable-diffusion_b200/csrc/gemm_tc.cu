@@ -954,7 +954,8 @@ extern "C" int sdb_gemm(const sdb_gemm_desc* d, sdb_stream_t stream) {
               p.rows_per_sample);
     p.stats = static_cast<double*>(d->stats_out);
     p.stats_halves = (p.rows_per_sample % 128 == 0) ? 1 : 2;
-    SDB_CUDA(cudaMemsetAsync(p.stats, 0, static_cast<size_t>(STAT_SLOTS) * p.n_samples * d->n * 2 * sizeof(double), st));
+    if (!d->stats_prezeroed)
+      SDB_CUDA(cudaMemsetAsync(p.stats, 0, static_cast<size_t>(STAT_SLOTS) * p.n_samples * d->n * 2 * sizeof(double), st));
   }
 
   int rc;

@@ -38,6 +38,7 @@ class GemmDesc(C.Structure):
         ("workspace", C.c_void_p),
         ("workspace_floats", C.c_int64),
         ("stats_out", C.c_void_p),
+        ("stats_prezeroed", C.c_int32),
     ]
 
 

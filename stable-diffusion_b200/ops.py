@@ -114,7 +114,11 @@ def gemm(a0, b, *, a1=None, a2=None, a3=None, nb=None, h=None, w=None, taps=1, b
     if want_stats and out_f32 is not None and act != ACT_GEGLU and (taps == 9 or rows_per_sample):
         rps = rows_per_sample if rows_per_sample else h * w
         if rps % 64 == 0 and n % 32 == 0 and M % rps == 0:
-            stats = torch.empty((4, M // rps, n, 2), dtype=torch.float64, device=a0.device)
+            stats = ARENA.take((4, M // rps, n, 2)) if ARENA is not None else None
+            if stats is not None:
+                d.stats_prezeroed = 1
+            else:
+                stats = torch.empty((4, M // rps, n, 2), dtype=torch.float64, device=a0.device)
             d.stats_out = _ptr(stats)
             out_f32._sdb_stats = stats   # travels with the tensor object (and, through ._base, with its views)
     d.splits = splits
@@ -147,6 +151,32 @@ def gemm(a0, b, *, a1=None, a2=None, a3=None, nb=None, h=None, w=None, taps=1, b
     if out_f16_lo is not None:
         return out_f16, out_f32, out_f16_lo
     return out_f16, out_f32
+
+
+class StatsArena:
+    """One pre-zeroed fp64 buffer per forward pass for all fused GroupNorm statistics (a single memset instead of one
+    per GEMM). reset() zeroes it and rewinds the bump pointer; gemm(want_stats=True) carves its [4, nb, n, 2] slice."""
+
+    def __init__(self, device, n_doubles=2 * 1024 * 1024):
+        self.buf = torch.zeros(n_doubles, dtype=torch.float64, device=device)
+        self.off = 0
+
+    def reset(self):
+        self.buf.zero_()
+        self.off = 0
+
+    def take(self, shape):
+        n = 1
+        for s_ in shape:
+            n *= s_
+        if self.off + n > self.buf.numel():
+            return None
+        v = self.buf[self.off: self.off + n].view(shape)
+        self.off += (n + 1) // 2 * 2
+        return v
+
+
+ARENA = None   # set by the model around a forward pass (UNetModel._forward_impl)
 
 
 def channel_stats(x):

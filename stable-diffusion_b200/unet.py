@@ -112,6 +112,7 @@ class UNetModel(nn.Module):
         self._ctx_kv = None
         self._kv_static = {}
         self._graphs = {}
+        self._arena = None
         self.use_cuda_graph = False   # replay one captured graph per UNet evaluation (set by the pipeline / bench)
         self.autotune = True          # graph mode: pick (block_n, split-K) per GEMM problem by measurement before capture
 
@@ -365,6 +366,17 @@ class UNetModel(nn.Module):
     # ------------------------------------------------------------------ forward
     def _forward_impl(self, x, t, kvs):
         """x NCHW fp32, t fp32 [nb], kvs from context_kv -> eps NCHW fp32. Pure kernel sequence (graph-capturable)."""
+        nb, _, H, Wd = x.shape
+        if self._arena is None:
+            self._arena = ops.StatsArena(x.device)
+        self._arena.reset()          # one memset for all fused GroupNorm statistics of this evaluation
+        ops.ARENA = self._arena
+        try:
+            return self._forward_body(x, t, kvs)
+        finally:
+            ops.ARENA = None
+
+    def _forward_body(self, x, t, kvs):
         nb, _, H, Wd = x.shape
         film = self._film(t)
         h, _ = ops.nchw_to_nhwc(x)
