@@ -311,3 +311,23 @@ def test_gemm_fused_groupnorm_stats_and_inkernel_splitk(S, cuda_dev):
     cat = torch.cat([a32.view(2, 8, 8, 192), b32.view(2, 8, 8, 64)], -1)
     yr = F.group_norm(cat.permute(0, 3, 1, 2), 32, gam, bet, 1e-6).permute(0, 2, 3, 1)
     assert rel_l2(y.float(), yr) < 6e-4
+
+
+def test_c_abi_rejects_bad_arguments(S, cuda_dev):
+    """Error behaviour of the boundary: non-zero return + message, surfaced as RuntimeError (never a silent fallback)."""
+    a = torch.zeros(128, 64, dtype=torch.float16, device=cuda_dev)
+    b = torch.zeros(64, 64, dtype=torch.float16, device=cuda_dev)
+    with pytest.raises(RuntimeError, match="taps"):
+        d = S.lib.GemmDesc()
+        d.a0, d.b, d.c0, d.nb, d.h, d.w, d.taps, d.n = a.data_ptr(), b.data_ptr(), 64, 1, 1, 128, 5, 64
+        d.out_f32 = torch.empty(128, 64, device=cuda_dev).data_ptr()
+        S.lib.check(S.lib.load().sdb_gemm(d, None), "sdb_gemm")
+    with pytest.raises(RuntimeError, match="multiple of 64"):
+        S.ops.gemm(torch.zeros(128, 40, dtype=torch.float16, device=cuda_dev),
+                   torch.zeros(64, 40, dtype=torch.float16, device=cuda_dev), want_f32=True)
+    with pytest.raises(RuntimeError, match="dpad"):
+        q = torch.zeros(1, 64, 96, dtype=torch.float16, device=cuda_dev)
+        S.ops.attention(q, q, torch.zeros(1, 96, 64, dtype=torch.float16, device=cuda_dev), heads=1, d=96, dpad=96,
+                        nq=64, nkv=64, scale=1.0)
+    with pytest.raises(RuntimeError, match="GEGLU"):
+        S.ops.gemm(a, torch.zeros(96, 64, dtype=torch.float16, device=cuda_dev), act=S.ops.ACT_GEGLU, want_f16=True)
