@@ -321,10 +321,11 @@ def run_gpu(args):
         line = {
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
             "config": {"workload": f"txt2img SD-v1-4 random-init, 512x512, 50 PLMS steps (51 UNet evals), CFG 7.5, "
                                    f"batch {B} per GPU", "parallelism": f"dp{world}", "l2": "weights 2.1 GB > 126 MB L2; "
                                    "no explicit flush inside a step (UNet-only timing flushes L2)",
+                       "arithmetic": "fp16 tensor-core operands, fp32 accumulate / residual stream / norms / softmax",
                        "algorithmic_tflop_per_image": (51 * 2 * UNET_GF_PER_SAMPLE + VAE_DEC_GF + 2 * CLIP_GF_PER_PROMPT) / 1e3},
             "unet_step_ms": unet_ms, "gpu_launches": int(launches),
             "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(ids_p.nbytes + un_p.nbytes + xT_p.nbytes),

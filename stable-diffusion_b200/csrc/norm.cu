@@ -346,7 +346,8 @@ extern "C" int sdb_layernorm(const float* x, int32_t rows, int32_t c, const floa
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SDB_CHECK(x && gamma && beta && (out_f16 || out_f32), "sdb_layernorm: null pointer");
   SDB_CHECK(c <= 32 * 48, "sdb_layernorm: C=%d too large", c);
-  int warps_per_block = 8;
+  // one warp per row; fewer warps per block at small row counts so the grid still covers the machine
+  int warps_per_block = rows >= 8 * 2 * sm_count() ? 8 : rows >= 4 * 2 * sm_count() ? 4 : rows >= 2 * 2 * sm_count() ? 2 : 1;
   int blocks = (rows + warps_per_block - 1) / warps_per_block;
   __half* o16 = static_cast<__half*>(out_f16);
   const int npl = (c + 31) / 32;
