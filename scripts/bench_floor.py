@@ -42,3 +42,11 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 torch.cuda._sleep(int(4e7)); e0.record()
 for _ in range(200): ops.layernorm(x, g, b)
 e1.record(); torch.cuda.synchronize(); print("layernorm 8192x320", e0.elapsed_time(e1) / 200 * 1000, "us (python-launch bound if > kernel)")
+# fused-statistics cost without the memset (arena path)
+ops.ARENA = ops.StatsArena(dev)
+r = rec(8192, 320, 320, rows_per_sample=4096, want_stats=True)
+print(f"{'linear 8192x320x320 +stats (arena)':36s} {t([r]):7.2f} us/launch")
+ops.ARENA.reset()
+r = rec(0, 320, 0, taps=9, hw=(2, 64, 64, 320), want_stats=True)
+print(f"{'conv 64x64 320->320 +stats (arena)':36s} {t([r]):7.2f} us/launch")
+ops.ARENA = None

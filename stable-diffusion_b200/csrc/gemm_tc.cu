@@ -596,7 +596,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");   // slots consumed before the next tile rewrites them
       }
     }
-    if (lane == 0) tma_store_wait<0>();
+    // smem may be released once the bulk stores have READ it; their global writes complete with the grid
+    if (lane == 0) tma_store_wait_read<0>();
     tc_fence_before();
   }
   __syncthreads();
