@@ -79,6 +79,8 @@ typedef struct sdb_gemm_desc {
                             the fp32 output, accumulated by the epilogue (zeroed by the call) — the GroupNorm statistics
                             of the tensor being produced, so no separate reduction pass reads it again */
   int32_t stats_prezeroed; /* non-zero: the caller already zeroed stats_out (one arena memset per forward pass) */
+  int32_t b_dynamic;       /* non-zero: b is an activation produced by the preceding kernel (e.g. V^T = W_v . X^T swaps
+                              the operand roles), so it must not be prefetched ahead of the programmatic-launch wait */
 } sdb_gemm_desc;
 
 int sdb_gemm(const sdb_gemm_desc* d, sdb_stream_t stream);

@@ -190,9 +190,14 @@ __global__ void __launch_bounds__(192)
           if ((kv >= p.nkv) || (p.causal && kv > qi)) t[c] = -INFINITY;
         }
       }
-      float m_raw = -INFINITY;
+      // 8 independent partial maxima / sums: a serial 64-deep FMNMX / FADD chain would expose ~4 cycles per element
+      // with only two softmax warps per scheduler to hide it
+      float mx[8];
 #pragma unroll
-      for (int c = 0; c < AKV; ++c) m_raw = fmaxf(m_raw, t[c]);
+      for (int i = 0; i < 8; ++i) mx[i] = t[i];
+#pragma unroll
+      for (int c = 8; c < AKV; ++c) mx[c & 7] = fmaxf(mx[c & 7], t[c]);
+      const float m_raw = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
       const float m_blk = m_raw * p.scale_log2;  // scale > 0
       if (j == 0) {
         m_used = m_blk;
@@ -218,14 +223,14 @@ __global__ void __launch_bounds__(192)
           if (need) m_used = m_new;
         }
       }
-      float sum = 0.f;
+      float sm[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       const float neg_m = -m_used;
 #pragma unroll
       for (int c = 0; c < AKV; ++c) {
         t[c] = fast_exp2(fmaf(t[c], p.scale_log2, neg_m));
-        sum += t[c];
+        sm[c & 7] += t[c];
       }
-      l += sum;
+      l += ((sm[0] + sm[1]) + (sm[2] + sm[3])) + ((sm[4] + sm[5]) + (sm[6] + sm[7]));
       if (j >= 2) mbar_wait(&pv_done[s], ((j - 2) >> 1) & 1);  // P buffer s was read by PV(j-2)
       uint8_t* prow = p_s + s * P_BYTES + r * 128;
 #pragma unroll

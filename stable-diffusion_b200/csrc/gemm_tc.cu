@@ -67,6 +67,7 @@ struct GemmArgs {
   double* stats;    // optional per-(sample, channel) {sum, sum of squares} of the fp32 output (GroupNorm statistics)
   int stats_halves;       // 1: the 128 rows of a tile belong to one sample; 2: rows 0-63 / 64-127 to two samples
   int n_samples;
+  int b_static;     // B is a weight matrix: safe to prefetch before griddepcontrol.wait
   int fast;         // outputs go through the TMA-store epilogue
   int bw, bh;       // store box: bw x bh x (32 / (bw*bh)) output pixels per epilogue warp
 };
@@ -259,7 +260,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       // PDL: the weight (B) tiles do not depend on the previous kernel — start streaming them for the first ring
       // pass of the first tile before waiting for the producer of the activations
       int npre = 0;
-      if (blockIdx.x < tiles_total) {
+      if (p.b_static && blockIdx.x < tiles_total) {
         const int rest0 = blockIdx.x / p.m_tiles;
         const int n_tile0 = rest0 % p.n_tiles;
         const int split0 = rest0 / p.n_tiles;
@@ -826,6 +827,7 @@ extern "C" int sdb_gemm(const sdb_gemm_desc* d, sdb_stream_t stream) {
   p.out_f16_lo = static_cast<__half*>(d->out_f16_lo);
   p.out_f32 = d->out_f32;
   p.act = d->act;
+  p.b_static = d->b_dynamic ? 0 : 1;
   const bool geglu = d->act == SDB_ACT_GEGLU;
   const int n_out = geglu ? d->n / 2 : d->n;
   p.ldo = d->ldo > 0 ? d->ldo : n_out;

@@ -39,6 +39,7 @@ class GemmDesc(C.Structure):
         ("workspace_floats", C.c_int64),
         ("stats_out", C.c_void_p),
         ("stats_prezeroed", C.c_int32),
+        ("b_dynamic", C.c_int32),
     ]
 
 

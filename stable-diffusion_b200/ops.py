@@ -56,7 +56,7 @@ def _chk32(t, name):
 def gemm(a0, b, *, a1=None, a2=None, a3=None, nb=None, h=None, w=None, taps=1, bias=None, film=None,
          rows_per_sample=0, residual=None, act=ACT_NONE, alpha=1.0, out_f16=None, out_f32=None, out_f16_lo=None,
          want_f16=False, want_f32=False, want_lo=False, n=None, block_n=0, splits=0, workspace=None,
-         want_stats=False):
+         want_stats=False, b_dynamic=False):
     """acc = A @ B^T with fused epilogue (see sdb_gemm in include/sdb200.h).
 
     a0 (, a1, a2, a3): fp16 [..., c_i] NHWC activations or plain [rows, c_i] matrices, concatenated along K.
@@ -110,6 +110,7 @@ def gemm(a0, b, *, a1=None, a2=None, a3=None, nb=None, h=None, w=None, taps=1, b
     d.out_f16, d.out_f32, d.out_f16_lo = _ptr(out_f16), _ptr(out_f32), _ptr(out_f16_lo)
     d.ldo = 0
     d.block_n = block_n
+    d.b_dynamic = 1 if b_dynamic else 0   # b produced by the previous kernel: no early (pre-dependency) prefetch
     stats = None
     if want_stats and out_f32 is not None and act != ACT_GEGLU and (taps == 9 or rows_per_sample):
         rps = rows_per_sample if rows_per_sample else h * w

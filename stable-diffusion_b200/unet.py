@@ -283,7 +283,7 @@ class UNetModel(nn.Module):
         qk3 = qk.view(nb, ntok, 2 * hd)
         if ntok % 8 == 0:
             # V^T straight out of the tensor cores by swapping the operand roles: [hd, M] = Wv . y^T
-            vt, _ = ops.gemm(s["w_v1"], y, want_f16=True)
+            vt, _ = ops.gemm(s["w_v1"], y, want_f16=True, b_dynamic=True)
             vt3 = vt.view(hd, nb, ntok).permute(1, 0, 2)                                   # [nb, hd, ntok] (strided view)
         else:  # TMA needs 16-byte aligned strides: tiny token counts go through an explicit transpose
             v, _ = ops.gemm(y, s["w_v1"], want_f16=True)

@@ -184,15 +184,15 @@ class AutoencoderKL(nn.Module):
             q = q_all.view(nb, n, c)[b]
             k = k_all.view(nb, n, c)[b]
             if n % 8 == 0:
-                vt, _ = ops.gemm(a["w_v"], hb, want_f16=True)                      # V^T [c, n]
+                vt, _ = ops.gemm(a["w_v"], hb, want_f16=True, b_dynamic=True)      # V^T [c, n]
             else:
                 v, _ = ops.gemm(hb, a["w_v"], want_f16=True)
                 vt = ops.transpose_f16(v.view(1, n, c))[0]
-            _, s = ops.gemm(q, k, want_f32=True)                                   # [n, n] fp32 logits
+            _, s = ops.gemm(q, k, want_f32=True, b_dynamic=True)                   # [n, n] fp32 logits
             p = ops.softmax_rows(s, float(int(c) ** -0.5))
             if npad != n:
                 raise NotImplementedError("VAE attention needs h*w % 8 == 0")
-            ops.gemm(p, vt.contiguous(), out_f16=o[b])
+            ops.gemm(p, vt.contiguous(), out_f16=o[b], b_dynamic=True)
         _, out = ops.gemm(o.view(-1, c), a["w_o"], bias=a["b_o"], residual=x.view(-1, c), want_f32=True,
                           rows_per_sample=n, want_stats=True)
         return out.view(nb, H, Wd, c)
