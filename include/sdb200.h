@@ -175,6 +175,26 @@ int sdb_sampler_step(const float* x, const float* eps2, int32_t guided, float sc
                      cond half of the guidance-doubled latent batch */, float* pred_x0, float* e_out,
                      sdb_stream_t stream);
 
+/*
+ * DPM-Solver++ (multistep, order <= 2, data prediction) update fused with classifier-free guidance and the
+ * noise -> x0 conversion: replaces model_wrapper.model_fn + DPM_Solver.data_prediction_fn +
+ * dpm_solver_first_update / multistep_dpm_solver_second_update
+ * (ldm/models/diffusion/dpm_solver/dpm_solver.py:321-346, 386-399, 504-533, 755-789).
+ *   e   = e_uncond + scale (e_cond - e_uncond)            (eps2 as in sdb_sampler_step)
+ *   m0  = (x - sigma_s e) / alpha_s                        -> m_out (the history entry for the next step)
+ *   order 1: x_t = c_x x - c_m m0                          c_x = sigma_t / sigma_s, c_m = alpha_t * expm1(-h)
+ *   order 2: x_t = c_x x - c_m m0 - (c_m / 2) inv_r0 (m0 - m_prev)      c_m = alpha_t * (exp(-h) - 1)
+ * The host computes the scalars in fp32 exactly as the reference's schedule tensors do.
+ */
+int sdb_dpm_solver_step(const float* x, const float* eps2, int32_t guided, float scale, float sigma_s, float alpha_s,
+                        int32_t order, const float* m_prev, float c_x, float c_m, float inv_r0, int64_t n,
+                        float* m_out, float* x_out, float* x_out2 /* optional second copy */, sdb_stream_t stream);
+
+/* Inpainting blend of the samplers' mask branch (plms.py:147-150, ddim.py:144-147), in place:
+ * img = img_orig * mask + (1 - mask) * img; mask fp32 [nb, 1 or c, hw]; img2: optional second copy of the result. */
+int sdb_mask_blend(const float* img_orig, const float* mask, int32_t mask_channels, int32_t nb, int32_t c, int64_t hw,
+                   float* img, float* img2, sdb_stream_t stream);
+
 /* VAE posterior sample + scale (distributions.py:24-37, ddpm.py:542-549): moments NHWC fp32 [rows, 8]
  * -> z NCHW. And image post-process clamp((x+1)/2,0,1)*255 -> uint8 NHWC (txt2img.py:314-324). */
 int sdb_vae_sample(const float* moments, const float* noise_nchw, int32_t nb, int32_t hw, float scale_factor,

@@ -387,3 +387,147 @@ def stochastic_encode(x0, t_index, noise, S=50):
     a = torch.tensor(sc["alphas"], dtype=torch.float32)
     s1 = torch.tensor(sc["sqrt_one_minus_alphas"], dtype=torch.float32)
     return torch.sqrt(a)[t_index] * x0 + s1[t_index] * noise
+
+
+# ------------------------------------------------------------------------ inpainting blend (mask path)
+def masked_plms_sample(model_fn, x_T, c, uc, scale, mask, x0, q_noises, S=50):
+    """plms.py:147-150: before every step `img = q_sample(x0, ts) * mask + (1 - mask) * img`; q_noises[i] is the
+    N(0,1) draw q_sample makes at loop iteration i (ddpm.py:274-277)."""
+    sched = register_schedule()
+    sa, s1 = sched["sqrt_alphas_cumprod"], sched["sqrt_one_minus_alphas_cumprod"]
+    sc = sampler_schedule(S)
+    time_range = np.flip(sc["timesteps"])
+    total = len(time_range)
+    img, old_eps, b = x_T, [], x_T.shape[0]
+    for i, step in enumerate(time_range):
+        index = total - i - 1
+        ts = torch.full((b,), int(step), dtype=torch.long)
+        ts_next = torch.full((b,), int(time_range[min(i + 1, total - 1)]), dtype=torch.long)
+        img_orig = sa[ts].reshape(b, 1, 1, 1) * x0 + s1[ts].reshape(b, 1, 1, 1) * q_noises[i]
+        img = img_orig * mask + (1. - mask) * img
+        e_t = _guided_eps(model_fn, img, ts, c, uc, scale)
+        if len(old_eps) == 0:
+            x_prev, _ = _x_prev(img, e_t, sc, index)
+            e_prime = (e_t + _guided_eps(model_fn, x_prev, ts_next, c, uc, scale)) / 2
+        elif len(old_eps) == 1:
+            e_prime = (3 * e_t - old_eps[-1]) / 2
+        elif len(old_eps) == 2:
+            e_prime = (23 * e_t - 16 * old_eps[-1] + 5 * old_eps[-2]) / 12
+        else:
+            e_prime = (55 * e_t - 59 * old_eps[-1] + 37 * old_eps[-2] - 9 * old_eps[-3]) / 24
+        img, _ = _x_prev(img, e_prime, sc, index)
+        old_eps.append(e_t)
+        if len(old_eps) >= 4:
+            old_eps.pop(0)
+    return img
+
+
+def masked_ddim_sample(model_fn, x_T, c, uc, scale, mask, x0, q_noises, S=50):
+    """ddim.py:144-147 (same blend, DDIM update)."""
+    sched = register_schedule()
+    sa, s1 = sched["sqrt_alphas_cumprod"], sched["sqrt_one_minus_alphas_cumprod"]
+    sc = sampler_schedule(S)
+    time_range = np.flip(sc["timesteps"])
+    total = len(time_range)
+    img, b = x_T, x_T.shape[0]
+    for i, step in enumerate(time_range):
+        index = total - i - 1
+        ts = torch.full((b,), int(step), dtype=torch.long)
+        img_orig = sa[ts].reshape(b, 1, 1, 1) * x0 + s1[ts].reshape(b, 1, 1, 1) * q_noises[i]
+        img = img_orig * mask + (1. - mask) * img
+        img, _ = _x_prev(img, _guided_eps(model_fn, img, ts, c, uc, scale), sc, index)
+    return img
+
+
+# ------------------------------------------------------------- DPM-Solver++ (multistep, order 2, data prediction)
+class DiscreteVPSchedule:
+    """NoiseScheduleVP('discrete', alphas_cumprod=...), dpm_solver.py:99-108, 125-156: log(alpha_t) is the piecewise
+    linear interpolant of 0.5*log(alphas_cumprod) over t_n = n/N, n = 1..N (extended linearly outside)."""
+
+    def __init__(self, alphas_cumprod):
+        self.log_alpha = 0.5 * torch.log(alphas_cumprod.float())
+        self.total_N = len(self.log_alpha)
+        self.T = 1.
+        self.t_array = torch.linspace(0., 1., self.total_N + 1)[1:]
+
+    def marginal_log_mean_coeff(self, t):
+        """interpolate_fn (dpm_solver.py:1132-1171) for a 1-D batch of abscissae: the two keypoints that bracket t
+        (the outermost segment outside the table), y0 + (t - x0) * (y1 - y0) / (x1 - x0) in fp32."""
+        xp, yp, K = self.t_array, self.log_alpha, self.total_N
+        out = torch.empty_like(t)
+        for n in range(t.numel()):
+            x = t[n]
+            x_idx = int((xp < x).sum())   # rank of x among the keypoints (a tie sorts x first, as in the reference)
+            if x_idx == 0:
+                lo = 0
+            elif x_idx == K:
+                lo = K - 2
+            else:
+                lo = x_idx - 1
+            out[n] = yp[lo] + (x - xp[lo]) * (yp[lo + 1] - yp[lo]) / (xp[lo + 1] - xp[lo])
+        return out
+
+    def marginal_alpha(self, t):
+        return torch.exp(self.marginal_log_mean_coeff(t))
+
+    def marginal_std(self, t):
+        return torch.sqrt(1. - torch.exp(2. * self.marginal_log_mean_coeff(t)))
+
+    def marginal_lambda(self, t):
+        lm = self.marginal_log_mean_coeff(t)
+        return lm - 0.5 * torch.log(1. - torch.exp(2. * lm))
+
+
+def dpm_solver_sample(model_fn, x_T, c, uc, scale, S=20, sched=None, record=None):
+    """DPMSolverSampler.sample (dpm_solver/sampler.py:55-82): model_wrapper(noise, classifier-free) +
+    DPM_Solver(predict_x0=True, thresholding=False).sample(steps=S, skip_type='time_uniform', method='multistep',
+    order=2, lower_order_final=True) (dpm_solver.py:321-346, 386-399, 504-550, 755-810, 965-1108)."""
+    sched = sched or register_schedule()
+    ns = DiscreteVPSchedule(sched["alphas_cumprod"])
+    b = x_T.shape[0]
+    t_0, t_T = 1. / ns.total_N, ns.T
+    timesteps = torch.linspace(t_T, t_0, S + 1)
+    ex = lambda v: v.reshape(b, 1, 1, 1)
+
+    def data_pred(x, t):
+        t_in = (t - 1. / ns.total_N) * 1000.
+        noise = _guided_eps(model_fn, x, t_in, c, uc, scale)
+        if record is not None:
+            record.append(noise)
+        return (x - ex(ns.marginal_std(t)) * noise) / ex(ns.marginal_alpha(t))
+
+    def first_update(x, s, t, m_s):
+        h = ns.marginal_lambda(t) - ns.marginal_lambda(s)
+        alpha_t = torch.exp(ns.marginal_log_mean_coeff(t))
+        return ex(ns.marginal_std(t) / ns.marginal_std(s)) * x - ex(alpha_t * torch.expm1(-h)) * m_s
+
+    def second_update(x, m_prev, t_prev, t):
+        m1, m0 = m_prev
+        t1, t0 = t_prev
+        l1, l0, lt = ns.marginal_lambda(t1), ns.marginal_lambda(t0), ns.marginal_lambda(t)
+        alpha_t = torch.exp(ns.marginal_log_mean_coeff(t))
+        h_0, h = l0 - l1, lt - l0
+        r0 = h_0 / h
+        D1_0 = ex(1. / r0) * (m0 - m1)
+        return (ex(ns.marginal_std(t) / ns.marginal_std(t0)) * x - ex(alpha_t * (torch.exp(-h) - 1.)) * m0
+                - 0.5 * ex(alpha_t * (torch.exp(-h) - 1.)) * D1_0)
+
+    x = x_T
+    vec_t = timesteps[0].expand(b)
+    m_list, t_list = [data_pred(x, vec_t)], [vec_t]
+    vec_t = timesteps[1].expand(b)
+    x = first_update(x, t_list[-1], vec_t, m_list[-1])
+    m_list.append(data_pred(x, vec_t))
+    t_list.append(vec_t)
+    for step in range(2, S + 1):
+        vec_t = timesteps[step].expand(b)
+        order = min(2, S + 1 - step) if S < 15 else 2
+        if order == 1:
+            x = first_update(x, t_list[-1], vec_t, m_list[-1])
+        else:
+            x = second_update(x, m_list, t_list, vec_t)
+        t_list[0], m_list[0] = t_list[1], m_list[1]
+        t_list[-1] = vec_t
+        if step < S:
+            m_list[-1] = data_pred(x, vec_t)
+    return x

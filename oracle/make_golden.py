@@ -166,6 +166,62 @@ def pipeline_goldens():
 
 
 @torch.no_grad()
+def samplers_ext_goldens():
+    """SURVEY 8(f) rows on the tiny model, run by the reference's own code: DPMSolverSampler
+    (dpm_solver/sampler.py + dpm_solver.py, multistep order 2, data prediction) and the mask (inpainting) branch
+    of PLMSSampler / DDIMSampler (plms.py:147-150, ddim.py:144-147) with the q_sample draws recorded."""
+    import contextlib
+    import io
+    ld = R.build_latent_diffusion(arch.TINY_UNET, arch.TINY_VAE)
+    usd = arch.random_state_dict(arch.unet_param_shapes(arch.TINY_UNET), UNET_SEED)
+    ld.model.diffusion_model.load_state_dict(usd, strict=True)
+    plms, ddim = R.build_samplers(ld)
+    from ldm.models.diffusion.dpm_solver import DPMSolverSampler
+    DPMSolverSampler.register_buffer = lambda s, n, a: setattr(s, n, a)
+    dpm = DPMSolverSampler(ld)
+    B, shape = 2, [4, 16, 16]
+    c, uc, x_T = gen((B, 77, 64), 400), gen((B, 77, 64), 401), gen((B, *shape), 402)
+    out = dict(c=c, uc=uc, x_T=x_T, unet_seed=UNET_SEED)
+    model_fn = lambda x, t, cc: O.unet_forward(usd, x, t, cc, num_heads=arch.TINY_UNET["num_heads"])
+    buf = io.StringIO()
+    for S, scale in ((20, 7.5), (10, 7.5), (15, 1.0)):
+        with contextlib.redirect_stdout(buf), contextlib.redirect_stderr(buf):
+            s_ref, _ = dpm.sample(S=S, conditioning=c, batch_size=B, shape=shape, verbose=False,
+                                  unconditional_guidance_scale=scale,
+                                  unconditional_conditioning=uc if scale != 1.0 else None, eta=0.0, x_T=x_T)
+        out[f"dpm{S}_s{scale}"] = s_ref
+        mine = O.dpm_solver_sample(model_fn, x_T, c, uc if scale != 1.0 else None, scale, S=S)
+        print(f"dpm-solver S={S} scale={scale}: sample std {float(s_ref.std()):.3f}; oracle rel {rel(mine, s_ref):.2e}")
+    # inpainting: mask (B,1,H,W) of 0/1 blocks, x0 = the latent to keep where mask == 1
+    mask = (gen((B, 1, 16, 16), 410) > 0).float()
+    x0 = gen((B, *shape), 411)
+    out.update(mask=mask, x0=x0)
+    real_randn_like = torch.randn_like
+    for name, smp, fn in (("plms", plms, O.masked_plms_sample), ("ddim", ddim, O.masked_ddim_sample)):
+        draws = []
+
+        def rec_randn_like(t, *a, **k):
+            r = real_randn_like(t, *a, **k)
+            draws.append(r.clone())
+            return r
+        torch.manual_seed(77)
+        torch.randn_like = rec_randn_like
+        try:
+            with contextlib.redirect_stdout(buf), contextlib.redirect_stderr(buf):
+                s_ref, _ = smp.sample(S=10, conditioning=c, batch_size=B, shape=shape, verbose=False,
+                                      unconditional_guidance_scale=7.5, unconditional_conditioning=uc, eta=0.0,
+                                      x_T=x_T, mask=mask, x0=x0)
+        finally:
+            torch.randn_like = real_randn_like
+        assert len(draws) == 10, len(draws)
+        out[f"masked_{name}10"] = s_ref
+        out[f"masked_{name}10_qnoise"] = torch.stack(draws)
+        mine = fn(model_fn, x_T, c, uc, 7.5, mask, x0, draws, S=10)
+        print(f"masked {name} S=10: oracle rel {rel(mine, s_ref):.2e}")
+    save("samplers_ext.pt", out)
+
+
+@torch.no_grad()
 def clip_goldens():
     """Third-party arithmetic (transformers CLIPTextModel): pinned against the installed transformers, random weights."""
     from transformers import CLIPTextConfig, CLIPTextModel
@@ -196,7 +252,7 @@ def clip_goldens():
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ["unet", "vae", "pipeline", "clip"]
+    which = sys.argv[1:] or ["unet", "vae", "pipeline", "clip", "samplers_ext"]
     if "unet" in which:
         unet_goldens()
     if "vae" in which:
@@ -205,3 +261,5 @@ if __name__ == "__main__":
         pipeline_goldens()
     if "clip" in which:
         clip_goldens()
+    if "samplers_ext" in which:
+        samplers_ext_goldens()

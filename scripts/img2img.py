@@ -39,13 +39,14 @@ def main():
     p.add_argument("--n_samples", type=int, default=2)
     p.add_argument("--scale", type=float, default=5.0)
     p.add_argument("--strength", type=float, default=0.75)
+    p.add_argument("--config", type=str, default="configs/stable-diffusion/v1-inference.yaml")
     p.add_argument("--ckpt", type=str, default="models/ldm/stable-diffusion-v1/model.ckpt")
     p.add_argument("--seed", type=int, default=42)
     p.add_argument("--size", type=int, default=512, help="side of the synthetic init image when --init-img is omitted")
     opt = p.parse_args()
     torch.manual_seed(opt.seed)
     device = torch.device("cuda")
-    model = load_model_from_config(opt.ckpt, device)
+    model = load_model_from_config(opt.config, opt.ckpt, device)
     pipe = pipeline.Img2Img(model, steps=opt.ddim_steps, scale=opt.scale, strength=opt.strength, eta=opt.ddim_eta)
     B = opt.n_samples
     if opt.init_img:

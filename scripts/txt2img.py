@@ -20,23 +20,14 @@ import sdb200  # noqa: E402
 from sdb200 import pipeline  # noqa: E402
 
 
-def load_model_from_config(ckpt, device, verbose=False):
-    """scripts/txt2img.py:49-66: torch.load(ckpt)["state_dict"] -> load_state_dict(strict=False) -> .cuda().eval()"""
-    model = pipeline.build_model()
+def load_model_from_config(config, ckpt, device, verbose=False):
+    """scripts/txt2img.py:49-66 via sdb200.checkpoint (pickled .ckpt or .safetensors, reference YAML or built-in v1)."""
     if ckpt and os.path.exists(ckpt):
-        print(f"Loading model from {ckpt}")
-        pl_sd = torch.load(ckpt, map_location="cpu", weights_only=False)
-        if "global_step" in pl_sd:
-            print(f"Global Step: {pl_sd['global_step']}")
-        m, u = model.load_state_dict(pl_sd["state_dict"], strict=False)
-        if len(m) > 0 and verbose:
-            print("missing keys:", m)
-        if len(u) > 0 and verbose:
-            print("unexpected keys:", u)
-        model = model.to(device)
-    else:
-        print("no checkpoint given: seeded random-init weights (images will be noise-like)")
-        pipeline.load_random_weights(model, device, gen_device=device)
+        cfg = config if (config and os.path.exists(config)) else {"model": pipeline.v1_model_config()}
+        return sdb200.checkpoint.load_model_from_config(cfg, ckpt, device=device, verbose=verbose)
+    print("no checkpoint given: seeded random-init weights (images will be noise-like)")
+    model = pipeline.build_model()
+    pipeline.load_random_weights(model, device, gen_device=device)
     return model.eval()
 
 
@@ -75,12 +66,12 @@ def main():
     p.add_argument("--precision", type=str, choices=["full", "autocast"], default="autocast")
     p.add_argument("--token_seed", type=int, default=1234, help="seed of the stand-in token ids (no tokenizer offline)")
     opt = p.parse_args()
-    if opt.dpm_solver or opt.laion400m:
-        raise NotImplementedError("--dpm_solver / --laion400m are outside the SD-v1 PLMS/DDIM hot path of this engine")
+    if opt.laion400m:
+        raise NotImplementedError("--laion400m (a different checkpoint/config) is outside the SD-v1 path of this engine")
     torch.manual_seed(opt.seed)           # seed_everything (txt2img.py:243)
     device = torch.device("cuda")
-    model = load_model_from_config(opt.ckpt, device)
-    pipe = pipeline.Txt2Img(model, sampler="plms" if opt.plms else "ddim", steps=opt.ddim_steps, scale=opt.scale,
+    model = load_model_from_config(opt.config, opt.ckpt, device)
+    pipe = pipeline.Txt2Img(model, sampler="dpm_solver" if opt.dpm_solver else ("plms" if opt.plms else "ddim"), steps=opt.ddim_steps, scale=opt.scale,
                             height=opt.H, width=opt.W, eta=opt.ddim_eta, f=opt.f, channels=opt.C)
     os.makedirs(opt.outdir, exist_ok=True)
     sample_path = os.path.join(opt.outdir, "samples")

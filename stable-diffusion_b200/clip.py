@@ -19,6 +19,7 @@ import torch.nn as nn
 from . import ops
 from .arch import SD_V1_CLIP, clip_param_shapes
 from .ops import ACT_QUICK_GELU
+from .util import adopt_state_dict
 
 
 class _Transformer(nn.Module):
@@ -31,12 +32,12 @@ class _Transformer(nn.Module):
     def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
                               error_msgs):
         o = self._owner
-        sub = {k[len(prefix):]: v for k, v in state_dict.items() if k.startswith(prefix)}
-        missing = [k for k in o.shapes if k not in sub]
-        if missing:
-            missing_keys.extend(prefix + k for k in missing)
+        # text_model.embeddings.position_ids is a buffer of older transformers versions (present in sd-v1 checkpoints)
+        sd = adopt_state_dict(o, state_dict, prefix, missing_keys, unexpected_keys, error_msgs,
+                              ignore=("text_model.embeddings.position_ids",))
+        if sd is None:
             return
-        o._host_sd = {k: sub[k] for k in o.shapes}
+        o._host_sd = sd
         if o.W is not None:
             o.pack_weights(o.W["device"])
 

@@ -201,6 +201,46 @@ __global__ void to_uint8_kernel(const float* __restrict__ x, size_t n, uint8_t* 
   }
 }
 
+// DPM-Solver++ multistep update in data-prediction form (dpm_solver.py:386-399, 504-533, 755-789), fp32 in the
+// reference's operation order: m0 = (x - sigma_s e) / alpha_s; order 1: x_t = c_x x - c_m m0;
+// order 2: x_t = c_x x - c_m m0 - (0.5 c_m) * (inv_r0 (m0 - m_prev))
+__global__ void dpm_solver_step_kernel(const float* __restrict__ x, const float* __restrict__ eps2, int guided,
+                                       float scale, float sigma_s, float alpha_s, int order,
+                                       const float* __restrict__ m_prev, float c_x, float c_m, float inv_r0, size_t n,
+                                       float* __restrict__ m_out, float* __restrict__ x_out,
+                                       float* __restrict__ x_out2) {
+  const float half_c_m = __fmul_rn(0.5f, c_m);
+  GRID_STRIDE(i, n) {
+    float e;
+    if (guided) {
+      float eu = eps2[i], ec = eps2[n + i];
+      e = __fadd_rn(eu, __fmul_rn(scale, __fsub_rn(ec, eu)));
+    } else {
+      e = eps2[i];
+    }
+    const float xv = x[i];
+    const float m0 = __fdiv_rn(__fsub_rn(xv, __fmul_rn(sigma_s, e)), alpha_s);
+    float xt = __fsub_rn(__fmul_rn(c_x, xv), __fmul_rn(c_m, m0));
+    if (order == 2) xt = __fsub_rn(xt, __fmul_rn(half_c_m, __fmul_rn(inv_r0, __fsub_rn(m0, m_prev[i]))));
+    if (m_out) m_out[i] = m0;
+    x_out[i] = xt;
+    if (x_out2) x_out2[i] = xt;
+  }
+}
+
+// inpainting blend (plms.py:147-150, ddim.py:144-147): img = img_orig * mask + (1 - mask) * img; the mask is
+// [b, 1, h, w] (broadcast over channels) or [b, c, h, w]
+__global__ void mask_blend_kernel(const float* __restrict__ img_orig, const float* __restrict__ mask, int bcast,
+                                  size_t n, size_t chw, size_t hw, float* __restrict__ img, float* __restrict__ img2) {
+  GRID_STRIDE(i, n) {
+    const size_t mi = bcast ? (i / chw) * hw + (i % hw) : i;
+    const float m = mask[mi];
+    const float v = __fadd_rn(__fmul_rn(img_orig[i], m), __fmul_rn(__fsub_rn(1.0f, m), img[i]));
+    img[i] = v;
+    if (img2) img2[i] = v;
+  }
+}
+
 __global__ void axpby2_kernel(const float* __restrict__ x, const float* __restrict__ y, float a, float b, size_t n,
                               float* __restrict__ out) {
   GRID_STRIDE(i, n) out[i] = __fadd_rn(__fmul_rn(a, x[i]), __fmul_rn(b, y[i]));
@@ -313,6 +353,27 @@ extern "C" int sdb_sampler_step(const float* x, const float* eps2, int32_t guide
   StepCoef k{a_t, a_prev, sigma_t, sqrt_one_minus_a_t};
   sampler_step_kernel<<<grid_for(n), 256, 0, ST>>>(x, eps2, guided, scale, order, h1, h2, h3, noise, k,
                                                    static_cast<size_t>(n), x_prev, x_prev2, pred_x0, e_out);
+  SDB_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int sdb_dpm_solver_step(const float* x, const float* eps2, int32_t guided, float scale, float sigma_s,
+                                   float alpha_s, int32_t order, const float* m_prev, float c_x, float c_m,
+                                   float inv_r0, int64_t n, float* m_out, float* x_out, float* x_out2,
+                                   sdb_stream_t stream) {
+  SDB_CHECK(x && eps2 && x_out && n > 0, "sdb_dpm_solver_step: bad arguments");
+  SDB_CHECK(order == 1 || (order == 2 && m_prev), "sdb_dpm_solver_step: order %d (2 needs the previous prediction)", order);
+  dpm_solver_step_kernel<<<grid_for(n), 256, 0, ST>>>(x, eps2, guided, scale, sigma_s, alpha_s, order, m_prev, c_x, c_m,
+                                                      inv_r0, static_cast<size_t>(n), m_out, x_out, x_out2);
+  SDB_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int sdb_mask_blend(const float* img_orig, const float* mask, int32_t mask_channels, int32_t nb, int32_t c,
+                              int64_t hw, float* img, float* img2, sdb_stream_t stream) {
+  SDB_CHECK(img_orig && mask && img && nb > 0 && c > 0 && hw > 0, "sdb_mask_blend: bad arguments");
+  SDB_CHECK(mask_channels == 1 || mask_channels == c, "sdb_mask_blend: mask has %d channels, latent %d", mask_channels, c);
+  const size_t n = static_cast<size_t>(nb) * c * hw;
+  mask_blend_kernel<<<grid_for(n), 256, 0, ST>>>(img_orig, mask, mask_channels == 1 ? 1 : 0, n,
+                                                 static_cast<size_t>(c) * hw, static_cast<size_t>(hw), img, img2);
   SDB_LAUNCH_CHECK();
   return 0;
 }

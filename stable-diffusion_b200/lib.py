@@ -84,6 +84,8 @@ SIGNATURES = {
     "sdb_axpby": ([_P, _F, _F, _L, _P, _P], C.c_int),
     "sdb_pointwise_small": ([_P, _L, _I, _I, _P, _P, _F, _P, _P], C.c_int),
     "sdb_embed_tokens": ([_P, _I, _I, _I, _I, _P, _P, _P, _P], C.c_int),
+    "sdb_dpm_solver_step": ([_P, _P, _I, _F, _F, _F, _I, _P, _F, _F, _F, _L, _P, _P, _P, _P], C.c_int),
+    "sdb_mask_blend": ([_P, _P, _I, _I, _I, _L, _P, _P, _P], C.c_int),
     "sdb_axpby2": ([_P, _P, _F, _F, _L, _P, _P], C.c_int),
 }
 

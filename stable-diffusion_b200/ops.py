@@ -440,6 +440,38 @@ def sampler_step(x, eps2, *, guided, scale, order, hist, noise, a_t, a_prev, sig
     return x_prev, pred_x0, e_out
 
 
+def dpm_solver_step(x, eps2, *, guided, scale, sigma_s, alpha_s, order, m_prev, c_x, c_m, inv_r0, x_out, dup=False):
+    """One fused CFG + data-prediction + DPM-Solver++ (2M) update; returns (x_out, m0). dup as in sampler_step."""
+    _chk32(x, "x")
+    _chk32(eps2, "eps2")
+    n = x.numel()
+    m_out = torch.empty_like(x)
+    xo2 = None
+    if dup:
+        assert x_out.numel() == 2 * n and x_out.is_contiguous()
+        xo2 = C.c_void_p(x_out.data_ptr() + 4 * n)
+    _l.check(_l.load().sdb_dpm_solver_step(_ptr(x), _ptr(eps2), 1 if guided else 0, scale, sigma_s, alpha_s, order,
+                                           _ptr(m_prev), c_x, c_m, inv_r0, n, _ptr(m_out), _ptr(x_out), xo2,
+                                           _stream()), "sdb_dpm_solver_step")
+    _count()
+    return x_out, m_out
+
+
+def mask_blend(img_orig, mask, img, b, dup=False):
+    """img[:b] = img_orig * mask + (1 - mask) * img[:b], in place; dup also writes the result to img[b:2b]."""
+    _chk32(img_orig, "img_orig")
+    _chk32(mask, "mask")
+    _chk32(img, "img")
+    nb, c = img_orig.shape[0], img_orig.shape[1]
+    hw = img_orig[0, 0].numel()
+    assert nb == b and mask.shape[0] == nb and mask[0, 0].numel() == hw, (img_orig.shape, mask.shape)
+    i2 = C.c_void_p(img.data_ptr() + 4 * img_orig.numel()) if dup else None
+    _l.check(_l.load().sdb_mask_blend(_ptr(img_orig), _ptr(mask), mask.shape[1], nb, c, hw, _ptr(img), i2, _stream()),
+             "sdb_mask_blend")
+    _count()
+    return img
+
+
 def axpby2(x, y, a, b):
     _chk32(x, "x")
     _chk32(y, "y")

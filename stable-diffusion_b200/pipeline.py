@@ -10,11 +10,22 @@ import torch
 
 from . import arch, ops
 from .diffusion import LatentDiffusion
-from .samplers import DDIMSampler, PLMSSampler
+from .samplers import DDIMSampler, DPMSolverSampler, PLMSSampler
 
 V1_PARAMS = dict(linear_start=0.00085, linear_end=0.0120, num_timesteps_cond=1, log_every_t=200, timesteps=1000,
                  first_stage_key="jpg", cond_stage_key="txt", image_size=64, channels=4, cond_stage_trainable=False,
                  conditioning_key="crossattn", monitor="val/loss_simple_ema", scale_factor=0.18215, use_ema=False)
+
+
+def v1_model_config(unet_cfg=None, vae_cfg=None, clip_cfg=None):
+    """The `model:` node of configs/stable-diffusion/v1-inference.yaml as a dict, with the reference's target names
+    (sdb200.checkpoint / LatentDiffusion map them onto the B200 classes)."""
+    return {"target": "ldm.models.diffusion.ddpm.LatentDiffusion", "params": dict(
+        V1_PARAMS,
+        unet_config={"target": "ldm.modules.diffusionmodules.openaimodel.UNetModel", "params": dict(unet_cfg or arch.SD_V1_UNET)},
+        first_stage_config={"target": "ldm.models.autoencoder.AutoencoderKL", "params": dict(vae_cfg or arch.SD_V1_VAE)},
+        cond_stage_config={"target": "ldm.modules.encoders.modules.FrozenCLIPEmbedder",
+                           "params": {"config": dict(clip_cfg or arch.SD_V1_CLIP)}})}
 
 
 def build_model(unet_cfg=None, vae_cfg=None, clip_cfg=None):
@@ -44,7 +55,7 @@ class Txt2Img:
     def __init__(self, model, sampler="plms", steps=50, scale=7.5, height=512, width=512, eta=0.0, f=8, channels=4,
                  cuda_graph=True):
         self.model = model
-        self.sampler = PLMSSampler(model) if sampler == "plms" else DDIMSampler(model)
+        self.sampler = {"plms": PLMSSampler, "ddim": DDIMSampler, "dpm_solver": DPMSolverSampler}[sampler](model)
         self.steps, self.scale, self.eta = steps, scale, eta
         self.shape = [channels, height // f, width // f]
         model.model.diffusion_model.use_cuda_graph = bool(cuda_graph)

@@ -1,6 +1,7 @@
-"""PLMS and DDIM samplers with the reference's API surface (ldm/models/diffusion/plms.py:10-236,
-ldm/models/diffusion/ddim.py:12-241): `Sampler(model, schedule="linear")`, `.make_schedule`, `.sample(...)
--> (samples, intermediates)`, DDIM's `.stochastic_encode` / `.decode`.
+"""PLMS, DDIM and DPM-Solver++ samplers with the reference's API surface (ldm/models/diffusion/plms.py:10-236,
+ldm/models/diffusion/ddim.py:12-241, ldm/models/diffusion/dpm_solver/sampler.py:8-82): `Sampler(model,
+schedule="linear")`, `.make_schedule`, `.sample(...) -> (samples, intermediates)`, DDIM's `.stochastic_encode` /
+`.decode`, and the `mask` / `x0` inpainting branch of the PLMS / DDIM loops (plms.py:147-150, ddim.py:144-147).
 
 The per-step update (classifier-free guidance + Adams-Bashforth / DDIM step, ~25 elementwise launches and four
 host->device scalar fills per step in the reference, plms.py:182-236) is ONE fused kernel (sdb_sampler_step) taking
@@ -102,10 +103,27 @@ class _SamplerBase:
             x_prev=x_prev, pred_x0=pred_x0, e_out=e_out, dup=self._guided)
         return xp, p0, e
 
+    def _blend_mask(self, x2, mask, x0, step, b):
+        """img = q_sample(x0, ts) * mask + (1 - mask) * img on the persistent (doubled) latent buffer, in place."""
+        ts = self._ts_cache.get((int(step), b))
+        if ts is None:
+            ts = self._ts_cache[(int(step), b)] = torch.full((b,), int(step), device=x2.device, dtype=torch.long)
+        img_orig = self.model.q_sample(x0, ts)
+        ops.mask_blend(img_orig.contiguous().float(), mask, x2, b, dup=self._guided)
+
+    @staticmethod
+    def _prep_mask(mask, x0, device):
+        if mask is None:
+            return None, None
+        return (mask.to(device=device, dtype=torch.float32).contiguous(),
+                x0.to(device=device, dtype=torch.float32).contiguous())
+
     def _check_args(self, **kw):
-        for k in ("mask", "x0", "score_corrector", "corrector_kwargs", "normals_sequence"):
+        for k in ("score_corrector", "corrector_kwargs", "normals_sequence"):
             if kw.get(k) is not None:
                 raise NotImplementedError(f"{k} is outside the txt2img/img2img hot path of this engine")
+        if kw.get("mask") is not None:
+            assert kw.get("x0") is not None   # plms.py:148 / ddim.py:145
         if kw.get("quantize_x0"):
             raise NotImplementedError("quantize_x0 needs a VQ first stage (not SD v1)")
         if kw.get("noise_dropout", 0.) != 0.:
@@ -135,15 +153,17 @@ class PLMSSampler(_SamplerBase):
         if verbose:
             print(f"Data shape for PLMS sampling is {size}")
         return self.plms_sampling(conditioning, size, callback=callback, img_callback=img_callback, x_T=x_T,
-                                  log_every_t=log_every_t, temperature=temperature,
+                                  log_every_t=log_every_t, temperature=temperature, mask=mask, x0=x0,
                                   unconditional_guidance_scale=unconditional_guidance_scale,
                                   unconditional_conditioning=unconditional_conditioning)
 
     @torch.no_grad()
     def plms_sampling(self, cond, shape, x_T=None, callback=None, img_callback=None, log_every_t=100,
-                      temperature=1., unconditional_guidance_scale=1., unconditional_conditioning=None, **kw):
+                      temperature=1., unconditional_guidance_scale=1., unconditional_conditioning=None, mask=None,
+                      x0=None, **kw):
         device = self.model.device
         b = shape[0]
+        mask, x0 = self._prep_mask(mask, x0, device)
         img = torch.randn(shape, device=device) if x_T is None else x_T.to(device=device, dtype=torch.float32)
         self._setup_guidance(cond, unconditional_conditioning, unconditional_guidance_scale, b)
         self._ts_cache = {}
@@ -156,6 +176,8 @@ class PLMSSampler(_SamplerBase):
         for i, step in enumerate(time_range):
             index = total_steps - i - 1
             step_next = time_range[min(i + 1, total_steps - 1)]
+            if mask is not None:
+                self._blend_mask(x2, mask, x0, step, b)
             eps2 = self._eval(x2, step, b)
             if len(old_eps) == 0:
                 # pseudo improved Euler: x_prev from e_t, second evaluation at t_next, e' = (e_t + e_t_next)/2
@@ -176,7 +198,7 @@ class PLMSSampler(_SamplerBase):
             if img_callback:
                 img_callback(pred_x0, i)
             if index % log_every_t == 0 or index == total_steps - 1:
-                intermediates["x_inter"].append(x2[:b])
+                intermediates["x_inter"].append(x2[:b].clone() if mask is not None else x2[:b])
                 intermediates["pred_x0"].append(pred_x0)
         return x2[:b].clone(), intermediates
 
@@ -199,13 +221,14 @@ class DDIMSampler(_SamplerBase):
         if verbose:
             print(f"Data shape for DDIM sampling is {size}, eta {eta}")
         return self.ddim_sampling(conditioning, size, callback=callback, img_callback=img_callback, x_T=x_T,
-                                  log_every_t=log_every_t, temperature=temperature,
+                                  log_every_t=log_every_t, temperature=temperature, mask=mask, x0=x0,
                                   unconditional_guidance_scale=unconditional_guidance_scale,
                                   unconditional_conditioning=unconditional_conditioning)
 
     def _run(self, img, cond, timesteps, scale, uc, temperature=1., callback=None, img_callback=None,
-             log_every_t=100, intermediates=None):
+             log_every_t=100, intermediates=None, mask=None, x0=None):
         b = img.shape[0]
+        mask, x0 = self._prep_mask(mask, x0, img.device)
         self._setup_guidance(cond, uc, scale, b)
         self._ts_cache = {}
         rep = 2 if self._guided else 1
@@ -214,6 +237,8 @@ class DDIMSampler(_SamplerBase):
         total_steps = time_range.shape[0]
         for i, step in enumerate(time_range):
             index = total_steps - i - 1
+            if mask is not None:
+                self._blend_mask(x2, mask, x0, step, b)
             eps2 = self._eval(x2, step, b)
             noise = None
             if self.ddim_sigmas[index] != 0:
@@ -224,18 +249,19 @@ class DDIMSampler(_SamplerBase):
             if img_callback:
                 img_callback(pred_x0, i)
             if intermediates is not None and (index % log_every_t == 0 or index == total_steps - 1):
-                intermediates["x_inter"].append(x2[:b])
+                intermediates["x_inter"].append(x2[:b].clone() if mask is not None else x2[:b])
                 intermediates["pred_x0"].append(pred_x0)
         return x2[:b].clone()
 
     @torch.no_grad()
     def ddim_sampling(self, cond, shape, x_T=None, callback=None, img_callback=None, log_every_t=100,
-                      temperature=1., unconditional_guidance_scale=1., unconditional_conditioning=None, **kw):
+                      temperature=1., unconditional_guidance_scale=1., unconditional_conditioning=None, mask=None,
+                      x0=None, **kw):
         device = self.model.device
         img = torch.randn(shape, device=device) if x_T is None else x_T.to(device=device, dtype=torch.float32)
         intermediates = {"x_inter": [img], "pred_x0": [img]}
         out = self._run(img, cond, self.ddim_timesteps, unconditional_guidance_scale, unconditional_conditioning,
-                        temperature, callback, img_callback, log_every_t, intermediates)
+                        temperature, callback, img_callback, log_every_t, intermediates, mask=mask, x0=x0)
         return out, intermediates
 
     @torch.no_grad()
@@ -258,3 +284,99 @@ class DDIMSampler(_SamplerBase):
         assert not use_original_steps
         timesteps = self.ddim_timesteps[:t_start]
         return self._run(x_latent.float(), cond, timesteps, unconditional_guidance_scale, unconditional_conditioning)
+
+
+class DiscreteVPSchedule:
+    """NoiseScheduleVP('discrete', alphas_cumprod=...) of the reference (dpm_solver.py:99-108, 125-156) on the host:
+    log alpha_t is the piecewise-linear interpolant (interpolate_fn, dpm_solver.py:1132-1171) of
+    0.5 log(alphas_cumprod) over t_n = n/N; everything in fp32 torch ops in the reference's order."""
+
+    def __init__(self, alphas_cumprod):
+        ac = torch.as_tensor(alphas_cumprod).detach().to("cpu", torch.float32)
+        self.log_alpha = 0.5 * torch.log(ac)
+        self.total_N = int(ac.numel())
+        self.T = 1.
+        self.t_array = torch.linspace(0., 1., self.total_N + 1)[1:]
+
+    def marginal_log_mean_coeff(self, t):
+        xp, yp, K = self.t_array, self.log_alpha, self.total_N
+        idx = torch.searchsorted(xp, t.contiguous(), right=False)       # keypoints strictly below t
+        lo = torch.where(idx == 0, torch.zeros_like(idx), torch.where(idx == K, torch.full_like(idx, K - 2), idx - 1))
+        return yp[lo] + (t - xp[lo]) * (yp[lo + 1] - yp[lo]) / (xp[lo + 1] - xp[lo])
+
+    def marginal_alpha(self, t):
+        return torch.exp(self.marginal_log_mean_coeff(t))
+
+    def marginal_std(self, t):
+        return torch.sqrt(1. - torch.exp(2. * self.marginal_log_mean_coeff(t)))
+
+    def marginal_lambda(self, t):
+        lm = self.marginal_log_mean_coeff(t)
+        return lm - 0.5 * torch.log(1. - torch.exp(2. * lm))
+
+
+def dpm_solver_plan(alphas_cumprod, steps, order=2, lower_order_final=True):
+    """Per-evaluation scalars of DPM_Solver.sample(steps, skip_type='time_uniform', method='multistep', order=2,
+    lower_order_final=True) in data-prediction mode (dpm_solver.py:965-1108, 504-533, 755-789): evaluation i happens at
+    continuous time t_i (model input (t_i - 1/N) * 1000, dpm_solver.py:278-287) and is followed by the update to t_{i+1}.
+    Returns a list of dicts {t_input, sigma_s, alpha_s, order, c_x, c_m, inv_r0}, python floats holding fp32 values."""
+    assert order == 2 and steps >= order
+    ns = DiscreteVPSchedule(alphas_cumprod)
+    ts = torch.linspace(ns.T, 1. / ns.total_N, steps + 1)
+    lam, la, sig = ns.marginal_lambda(ts), ns.marginal_log_mean_coeff(ts), ns.marginal_std(ts)
+    alpha = torch.exp(la)
+    t_in = (ts - 1. / ns.total_N) * 1000.
+    plan = []
+    for i in range(steps):                      # update from t_i to t_{i+1}; "step" of the reference loop = i + 1
+        step = i + 1
+        o = 1 if i == 0 else (min(order, steps + 1 - step) if (lower_order_final and steps < 15) else order)
+        h = lam[i + 1] - lam[i]
+        e = dict(t_input=float(t_in[i]), sigma_s=float(sig[i]), alpha_s=float(alpha[i]), order=o,
+                 c_x=float(sig[i + 1] / sig[i]), inv_r0=0.0)
+        if o == 1:
+            e["c_m"] = float(alpha[i + 1] * torch.expm1(-h))
+        else:
+            r0 = (lam[i] - lam[i - 1]) / h
+            e["c_m"] = float(alpha[i + 1] * (torch.exp(-h) - 1.))
+            e["inv_r0"] = float(1. / r0)
+        plan.append(e)
+    return plan
+
+
+class DPMSolverSampler(_SamplerBase):
+    """dpm_solver/sampler.py:8-82: DPM-Solver++ multistep order 2 on the model's discrete schedule with classifier-free
+    guidance. Each step is one UNet evaluation (float timestep) + ONE fused kernel (guidance, eps -> x0, update)."""
+    name = "dpm_solver"
+
+    def __init__(self, model, **kwargs):
+        super().__init__(model, **kwargs)
+        self.alphas_cumprod = model.alphas_cumprod.detach().to("cpu", torch.float32)
+
+    @torch.no_grad()
+    def sample(self, S, batch_size, shape, conditioning=None, callback=None, normals_sequence=None,
+               img_callback=None, quantize_x0=False, eta=0., mask=None, x0=None, temperature=1., noise_dropout=0.,
+               score_corrector=None, corrector_kwargs=None, verbose=True, x_T=None, log_every_t=100,
+               unconditional_guidance_scale=1., unconditional_conditioning=None, **kwargs):
+        if conditioning is not None and conditioning.shape[0] != batch_size:
+            print(f"Warning: Got {conditioning.shape[0]} conditionings but batch-size is {batch_size}")
+        C, H, W = shape
+        device = self.model.betas.device
+        img = torch.randn((batch_size, C, H, W), device=device) if x_T is None else x_T.to(device=device, dtype=torch.float32)
+        b = batch_size
+        self._setup_guidance(conditioning, unconditional_conditioning, unconditional_guidance_scale, b)
+        plan = dpm_solver_plan(self.alphas_cumprod, S)
+        rep = 2 if self._guided else 1
+        x2 = img.repeat(rep, 1, 1, 1).contiguous() if rep == 2 else img.contiguous().clone()
+        m_prev = None
+        for i, p in enumerate(plan):
+            ts = torch.full((x2.shape[0],), p["t_input"], device=device, dtype=torch.float32)
+            eps2 = self.model.apply_model(x2, ts, self._c_in)
+            x2, m_prev = ops.dpm_solver_step(
+                x2[:b], eps2, guided=self._guided, scale=self._scale, sigma_s=p["sigma_s"], alpha_s=p["alpha_s"],
+                order=p["order"], m_prev=m_prev, c_x=p["c_x"], c_m=p["c_m"], inv_r0=p["inv_r0"],
+                x_out=torch.empty_like(x2), dup=self._guided)
+            if callback:
+                callback(i)
+            if img_callback:
+                img_callback(m_prev, i)
+        return x2[:b].clone(), None

@@ -18,6 +18,7 @@ import torch.nn as nn
 from . import ops
 from .arch import unet_param_shapes, unet_plan
 from .ops import ACT_GEGLU, ACT_SILU
+from .util import adopt_state_dict
 
 
 def _dpad(d):
@@ -119,15 +120,10 @@ class UNetModel(nn.Module):
     # ------------------------------------------------------------------ weights
     def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
                               error_msgs):
-        sub = {k[len(prefix):]: v for k, v in state_dict.items() if k.startswith(prefix)}
-        missing = [k for k in self.shapes if k not in sub]
-        if missing:
-            missing_keys.extend(prefix + k for k in missing)
+        sd = adopt_state_dict(self, state_dict, prefix, missing_keys, unexpected_keys, error_msgs)
+        if sd is None:
             return
-        for k in sub:
-            if k not in self.shapes:
-                unexpected_keys.append(prefix + k)
-        self._host_sd = {k: sub[k] for k in self.shapes}
+        self._host_sd = sd
         if self.W is not None:
             self.pack_weights(self.W["device"])
 

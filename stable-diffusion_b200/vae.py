@@ -14,6 +14,7 @@ import torch.nn as nn
 from . import ops
 from .arch import vae_param_shapes
 from .unet import _pack_conv3, _pack_conv3_padk
+from .util import adopt_state_dict
 
 
 class DiagonalGaussianDistribution:
@@ -61,13 +62,10 @@ class AutoencoderKL(nn.Module):
     # ------------------------------------------------------------------ weights
     def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
                               error_msgs):
-        sub = {k[len(prefix):]: v for k, v in state_dict.items() if k.startswith(prefix)}
-        missing = [k for k in self.shapes if k not in sub]
-        if missing:
-            missing_keys.extend(prefix + k for k in missing)
+        sd = adopt_state_dict(self, state_dict, prefix, missing_keys, unexpected_keys, error_msgs, ignore=("loss.",))
+        if sd is None:
             return
-        unexpected_keys.extend(prefix + k for k in sub if k not in self.shapes and not k.startswith("loss."))
-        self._host_sd = {k: sub[k] for k in self.shapes}
+        self._host_sd = sd
         if self.W is not None:
             self.pack_weights(self.W["device"])
 

@@ -113,7 +113,10 @@ def test_sampler_schedules_on_host():
     assert float(d.ddim_sigmas.max()) > 0
     with pytest.raises(NotImplementedError):
         sdb200.PLMSSampler(Facade()).sample(S=10, batch_size=1, shape=[4, 8, 8], conditioning=torch.zeros(1, 77, 64),
-                                            mask=torch.ones(1), x0=torch.zeros(1), verbose=False)
+                                            score_corrector=object(), verbose=False)
+    with pytest.raises(AssertionError):      # mask without x0 (plms.py:148)
+        sdb200.PLMSSampler(Facade()).sample(S=10, batch_size=1, shape=[4, 8, 8], conditioning=torch.zeros(1, 77, 64),
+                                            mask=torch.ones(1, 1, 8, 8), verbose=False)
 
 
 def test_shard_ranges_and_noise():
