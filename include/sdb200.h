@@ -169,7 +169,10 @@ int sdb_silu_f16(const float* x, int64_t n, void* out_f16, sdb_stream_t stream);
  *   pred_x0 = (x - sqrt(1-a_t) e') / sqrt(a_t);  x_prev = sqrt(a_prev) pred_x0 + sqrt(1-a_prev-sigma^2) e' + sigma*noise
  * coef = {a_t, a_prev, sigma_t, sqrt_one_minus_a_t}; e_t is written to e_out (for the multistep history).
  */
-int sdb_sampler_step(const float* x, const float* eps2, int32_t guided, float scale, int32_t order, const float* h1,
+int sdb_sampler_step(const float* x, const float* eps2, const float* eps_cond /* NULL: eps2 + n. Otherwise the
+                     conditional half lives elsewhere - e.g. in the peer GPU's buffer mapped over NVLink (CFG halves
+                     evaluated on two GPUs): the exchange is then the kernel's own peer loads */,
+                     int32_t guided, float scale, int32_t order, const float* h1,
                      const float* h2, const float* h3, const float* noise, float a_t, float a_prev, float sigma_t,
                      float sqrt_one_minus_a_t, int64_t n, float* x_prev, float* x_prev2 /* optional second copy: the
                      cond half of the guidance-doubled latent batch */, float* pred_x0, float* e_out,
@@ -186,7 +189,8 @@ int sdb_sampler_step(const float* x, const float* eps2, int32_t guided, float sc
  *   order 2: x_t = c_x x - c_m m0 - (c_m / 2) inv_r0 (m0 - m_prev)      c_m = alpha_t * (exp(-h) - 1)
  * The host computes the scalars in fp32 exactly as the reference's schedule tensors do.
  */
-int sdb_dpm_solver_step(const float* x, const float* eps2, int32_t guided, float scale, float sigma_s, float alpha_s,
+int sdb_dpm_solver_step(const float* x, const float* eps2, const float* eps_cond /* as in sdb_sampler_step */,
+                        int32_t guided, float scale, float sigma_s, float alpha_s,
                         int32_t order, const float* m_prev, float c_x, float c_m, float inv_r0, int64_t n,
                         float* m_out, float* x_out, float* x_out2 /* optional second copy */, sdb_stream_t stream);
 

@@ -134,8 +134,8 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, int n, in
 struct StepCoef {
   float a_t, a_prev, sigma_t, sqrt_one_minus_a_t;
 };
-__global__ void sampler_step_kernel(const float* __restrict__ x, const float* __restrict__ eps2, int guided,
-                                    float scale, int order, const float* __restrict__ h1,
+__global__ void sampler_step_kernel(const float* __restrict__ x, const float* __restrict__ eps2,
+                                    const float* __restrict__ eps_cond, int guided, float scale, int order, const float* __restrict__ h1,
                                     const float* __restrict__ h2, const float* __restrict__ h3,
                                     const float* __restrict__ noise, StepCoef k, size_t n, float* __restrict__ x_prev,
                                     float* __restrict__ x_prev2, float* __restrict__ pred_x0,
@@ -147,7 +147,7 @@ __global__ void sampler_step_kernel(const float* __restrict__ x, const float* __
   GRID_STRIDE(i, n) {
     float e_t;
     if (guided) {
-      float eu = eps2[i], ec = eps2[n + i];
+      float eu = eps2[i], ec = eps_cond[i];
       e_t = __fadd_rn(eu, __fmul_rn(scale, __fsub_rn(ec, eu)));
     } else {
       e_t = eps2[i];
@@ -204,8 +204,8 @@ __global__ void to_uint8_kernel(const float* __restrict__ x, size_t n, uint8_t* 
 // DPM-Solver++ multistep update in data-prediction form (dpm_solver.py:386-399, 504-533, 755-789), fp32 in the
 // reference's operation order: m0 = (x - sigma_s e) / alpha_s; order 1: x_t = c_x x - c_m m0;
 // order 2: x_t = c_x x - c_m m0 - (0.5 c_m) * (inv_r0 (m0 - m_prev))
-__global__ void dpm_solver_step_kernel(const float* __restrict__ x, const float* __restrict__ eps2, int guided,
-                                       float scale, float sigma_s, float alpha_s, int order,
+__global__ void dpm_solver_step_kernel(const float* __restrict__ x, const float* __restrict__ eps2,
+                                       const float* __restrict__ eps_cond, int guided, float scale, float sigma_s, float alpha_s, int order,
                                        const float* __restrict__ m_prev, float c_x, float c_m, float inv_r0, size_t n,
                                        float* __restrict__ m_out, float* __restrict__ x_out,
                                        float* __restrict__ x_out2) {
@@ -213,7 +213,7 @@ __global__ void dpm_solver_step_kernel(const float* __restrict__ x, const float*
   GRID_STRIDE(i, n) {
     float e;
     if (guided) {
-      float eu = eps2[i], ec = eps2[n + i];
+      float eu = eps2[i], ec = eps_cond[i];
       e = __fadd_rn(eu, __fmul_rn(scale, __fsub_rn(ec, eu)));
     } else {
       e = eps2[i];
@@ -343,7 +343,8 @@ extern "C" int sdb_timestep_embedding(const float* t, int32_t n, int32_t dim, fl
   SDB_LAUNCH_CHECK();
   return 0;
 }
-extern "C" int sdb_sampler_step(const float* x, const float* eps2, int32_t guided, float scale, int32_t order,
+extern "C" int sdb_sampler_step(const float* x, const float* eps2, const float* eps_cond, int32_t guided, float scale,
+                                int32_t order,
                                 const float* h1, const float* h2, const float* h3, const float* noise, float a_t,
                                 float a_prev, float sigma_t, float sqrt_one_minus_a_t, int64_t n, float* x_prev,
                                 float* x_prev2, float* pred_x0, float* e_out, sdb_stream_t stream) {
@@ -351,18 +352,21 @@ extern "C" int sdb_sampler_step(const float* x, const float* eps2, int32_t guide
   SDB_CHECK(order >= 0 && order <= 4, "sdb_sampler_step: order %d", order);
   SDB_CHECK((order == 0) || h1, "sdb_sampler_step: missing history");
   StepCoef k{a_t, a_prev, sigma_t, sqrt_one_minus_a_t};
-  sampler_step_kernel<<<grid_for(n), 256, 0, ST>>>(x, eps2, guided, scale, order, h1, h2, h3, noise, k,
+  if (!eps_cond) eps_cond = eps2 + n;   // [e_uncond; e_cond] contiguous
+  sampler_step_kernel<<<grid_for(n), 256, 0, ST>>>(x, eps2, eps_cond, guided, scale, order, h1, h2, h3, noise, k,
                                                    static_cast<size_t>(n), x_prev, x_prev2, pred_x0, e_out);
   SDB_LAUNCH_CHECK();
   return 0;
 }
-extern "C" int sdb_dpm_solver_step(const float* x, const float* eps2, int32_t guided, float scale, float sigma_s,
+extern "C" int sdb_dpm_solver_step(const float* x, const float* eps2, const float* eps_cond, int32_t guided, float scale,
+                                   float sigma_s,
                                    float alpha_s, int32_t order, const float* m_prev, float c_x, float c_m,
                                    float inv_r0, int64_t n, float* m_out, float* x_out, float* x_out2,
                                    sdb_stream_t stream) {
   SDB_CHECK(x && eps2 && x_out && n > 0, "sdb_dpm_solver_step: bad arguments");
   SDB_CHECK(order == 1 || (order == 2 && m_prev), "sdb_dpm_solver_step: order %d (2 needs the previous prediction)", order);
-  dpm_solver_step_kernel<<<grid_for(n), 256, 0, ST>>>(x, eps2, guided, scale, sigma_s, alpha_s, order, m_prev, c_x, c_m,
+  if (!eps_cond) eps_cond = eps2 + n;
+  dpm_solver_step_kernel<<<grid_for(n), 256, 0, ST>>>(x, eps2, eps_cond, guided, scale, sigma_s, alpha_s, order, m_prev, c_x, c_m,
                                                       inv_r0, static_cast<size_t>(n), m_out, x_out, x_out2);
   SDB_LAUNCH_CHECK();
   return 0;

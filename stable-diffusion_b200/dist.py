@@ -66,3 +66,60 @@ def gather_images(img: torch.Tensor, dst: int = 0):
     bufs = [torch.empty_like(img) for _ in range(world)] if rank == dst else None
     dist.gather(img, bufs, dst=dst)
     return torch.cat(bufs, 0) if rank == dst else None
+
+
+class CFGParallel:
+    """Latency mode: the two halves of a classifier-free-guided evaluation (plms.py:182-186,
+    ddim.py:174-178) run on TWO GPUs — group rank 0 evaluates the unconditional batch, rank 1 the conditional one —
+    and the eps halves meet in the fused sampler-step kernel, which both ranks execute identically (bit-exact
+    arithmetic), so the latents stay in lock-step without any further traffic.
+
+    mode "p2p":  each rank publishes its eps into a symmetric (peer-mapped) buffer, a device-side barrier follows, and
+                 the step kernel itself loads the other half straight from the peer GPU over NVLink (`eps_cond` /
+                 `eps2` of sdb_sampler_step point into peer memory): the exchange is fused into the compute kernel.
+                 Two alternating slots make the publish of evaluation k+1 safe against a late reader of evaluation k.
+    mode "nccl": all_gather_into_tensor of the two halves, then the ordinary step kernel (works with gloo on CPU
+                 tensors too: the host-logic test).
+    """
+
+    def __init__(self, group=None, mode="p2p", device=None, max_numel=8 * 4 * 96 * 96, barrier_timeout_ms=20000):
+        self.group = group if group is not None else dist.group.WORLD
+        assert dist.get_world_size(self.group) == 2, "CFG-parallel pairs exactly two ranks"
+        self.role = dist.get_rank(self.group)          # 0: unconditional half, 1: conditional half
+        self.mode = mode
+        self.device = device
+        self.evals = 0
+        self._timeout = barrier_timeout_ms
+        self._gather = {}
+        if mode == "p2p":
+            import torch.distributed._symmetric_memory as symm_mem
+            self._pub = symm_mem.empty((2, max_numel), dtype=torch.float32, device=device)
+            self._hdl = symm_mem.rendezvous(self._pub, self.group)
+            self._peer = self._hdl.get_buffer(1 - self.role, (2, max_numel), torch.float32)
+            self.max_numel = max_numel
+        elif mode != "nccl":
+            raise ValueError(f"unknown CFG-parallel mode {mode!r}")
+
+    def select(self, uncond, cond):
+        """This rank's half of the conditioning."""
+        return uncond if self.role == 0 else cond
+
+    def exchange(self, eps_local):
+        """eps of this rank's half -> (eps_uncond_or_pair, eps_cond_or_None) for ops.sampler_step / dpm_solver_step."""
+        n = eps_local.numel()
+        k = self.evals
+        self.evals += 1
+        if self.mode == "nccl":
+            buf = self._gather.get((n, eps_local.device))
+            if buf is None:
+                buf = self._gather[(n, eps_local.device)] = torch.empty((2,) + tuple(eps_local.shape), dtype=eps_local.dtype,
+                                                                        device=eps_local.device)
+            dist.all_gather_into_tensor(buf.view(-1), eps_local.contiguous().view(-1), group=self.group)
+            return buf.flatten(0, 1), None
+        assert n <= self.max_numel, (n, self.max_numel)
+        slot = k & 1
+        self._pub[slot, :n].copy_(eps_local.reshape(-1))            # publish (local write)
+        self._hdl.barrier(channel=slot, timeout_ms=self._timeout)    # both halves published and visible
+        mine = self._pub[slot, :n].view(eps_local.shape)
+        peer = self._peer[slot, :n].view(eps_local.shape)            # peer GPU memory, read by the step kernel
+        return (mine, peer) if self.role == 0 else (peer, mine)

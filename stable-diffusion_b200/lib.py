@@ -78,13 +78,13 @@ SIGNATURES = {
     "sdb_timestep_embedding_f32": ([_P, _I, _I, _F, _P, _P], C.c_int),
     "sdb_linear_small": ([_P, _I, _I, _P, _I, _P, _I, _P, _P, _P], C.c_int),
     "sdb_silu_f16": ([_P, _L, _P, _P], C.c_int),
-    "sdb_sampler_step": ([_P, _P, _I, _F, _I, _P, _P, _P, _P, _F, _F, _F, _F, _L, _P, _P, _P, _P, _P], C.c_int),
+    "sdb_sampler_step": ([_P, _P, _P, _I, _F, _I, _P, _P, _P, _P, _F, _F, _F, _F, _L, _P, _P, _P, _P, _P], C.c_int),
     "sdb_vae_sample": ([_P, _P, _I, _I, _F, _P, _P], C.c_int),
     "sdb_to_uint8": ([_P, _L, _P, _P], C.c_int),
     "sdb_axpby": ([_P, _F, _F, _L, _P, _P], C.c_int),
     "sdb_pointwise_small": ([_P, _L, _I, _I, _P, _P, _F, _P, _P], C.c_int),
     "sdb_embed_tokens": ([_P, _I, _I, _I, _I, _P, _P, _P, _P], C.c_int),
-    "sdb_dpm_solver_step": ([_P, _P, _I, _F, _F, _F, _I, _P, _F, _F, _F, _L, _P, _P, _P, _P], C.c_int),
+    "sdb_dpm_solver_step": ([_P, _P, _P, _I, _F, _F, _F, _I, _P, _F, _F, _F, _L, _P, _P, _P, _P], C.c_int),
     "sdb_mask_blend": ([_P, _P, _I, _I, _I, _L, _P, _P, _P], C.c_int),
     "sdb_axpby2": ([_P, _P, _F, _F, _L, _P, _P], C.c_int),
 }

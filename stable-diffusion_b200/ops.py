@@ -416,7 +416,7 @@ def linear_small(x, w, bias=None, act=ACT_NONE, want_f16=False):
 
 
 def sampler_step(x, eps2, *, guided, scale, order, hist, noise, a_t, a_prev, sigma_t, sqrt_one_minus_a_t,
-                 x_prev=None, pred_x0=None, e_out=None, dup=False):
+                 x_prev=None, pred_x0=None, e_out=None, dup=False, eps_cond=None):
     """One fused CFG + PLMS/DDIM update. x: [b,...] fp32; eps2: [2b,...] if guided else [b,...].
     dup: x_prev is a [2b,...] buffer and both halves receive the new latent (the next step's doubled batch)."""
     _chk32(x, "x")
@@ -432,7 +432,7 @@ def sampler_step(x, eps2, *, guided, scale, order, hist, noise, a_t, a_prev, sig
         assert x_prev.numel() == 2 * n and x_prev.is_contiguous()
         xp2 = C.c_void_p(x_prev.data_ptr() + 4 * n)
     h = list(hist) + [None] * (3 - len(hist))
-    _l.check(_l.load().sdb_sampler_step(_ptr(x), _ptr(eps2), 1 if guided else 0, scale, order, _ptr(h[0]),
+    _l.check(_l.load().sdb_sampler_step(_ptr(x), _ptr(eps2), _ptr(eps_cond), 1 if guided else 0, scale, order, _ptr(h[0]),
                                         _ptr(h[1]), _ptr(h[2]), _ptr(noise), a_t, a_prev, sigma_t,
                                         sqrt_one_minus_a_t, n, _ptr(x_prev), xp2, _ptr(pred_x0), _ptr(e_out),
                                         _stream()), "sdb_sampler_step")
@@ -440,7 +440,8 @@ def sampler_step(x, eps2, *, guided, scale, order, hist, noise, a_t, a_prev, sig
     return x_prev, pred_x0, e_out
 
 
-def dpm_solver_step(x, eps2, *, guided, scale, sigma_s, alpha_s, order, m_prev, c_x, c_m, inv_r0, x_out, dup=False):
+def dpm_solver_step(x, eps2, *, guided, scale, sigma_s, alpha_s, order, m_prev, c_x, c_m, inv_r0, x_out, dup=False,
+                    eps_cond=None):
     """One fused CFG + data-prediction + DPM-Solver++ (2M) update; returns (x_out, m0). dup as in sampler_step."""
     _chk32(x, "x")
     _chk32(eps2, "eps2")
@@ -450,7 +451,7 @@ def dpm_solver_step(x, eps2, *, guided, scale, sigma_s, alpha_s, order, m_prev, 
     if dup:
         assert x_out.numel() == 2 * n and x_out.is_contiguous()
         xo2 = C.c_void_p(x_out.data_ptr() + 4 * n)
-    _l.check(_l.load().sdb_dpm_solver_step(_ptr(x), _ptr(eps2), 1 if guided else 0, scale, sigma_s, alpha_s, order,
+    _l.check(_l.load().sdb_dpm_solver_step(_ptr(x), _ptr(eps2), _ptr(eps_cond), 1 if guided else 0, scale, sigma_s, alpha_s, order,
                                            _ptr(m_prev), c_x, c_m, inv_r0, n, _ptr(m_out), _ptr(x_out), xo2,
                                            _stream()), "sdb_dpm_solver_step")
     _count()

@@ -51,10 +51,11 @@ def make_ddim_sampling_parameters(alphacums, ddim_timesteps, eta, verbose=True):
 class _SamplerBase:
     name = "sampler"
 
-    def __init__(self, model, schedule="linear", **kwargs):
+    def __init__(self, model, schedule="linear", cfg_parallel=None, **kwargs):
         self.model = model
         self.ddpm_num_timesteps = model.num_timesteps
         self.schedule = schedule
+        self.cfg_parallel = cfg_parallel   # dist.CFGParallel: guidance halves on two GPUs (latency mode)
 
     # -- schedule (host side; fp32 values exactly as the reference's device tensors hold them)
     def make_schedule(self, ddim_num_steps, ddim_discretize="uniform", ddim_eta=0., verbose=True):
@@ -76,7 +77,12 @@ class _SamplerBase:
         self._scale = float(scale)
         if isinstance(cond, dict):
             raise NotImplementedError("dict conditioning (hybrid/concat) is outside the SD-v1 crossattn path")
-        self._c_in = torch.cat([uc, cond]).contiguous() if self._guided else cond.contiguous()
+        self._split = self._guided and self.cfg_parallel is not None
+        if self._split:
+            self._c_in = self.cfg_parallel.select(uc, cond).contiguous()   # this GPU evaluates one half only
+        else:
+            self._c_in = torch.cat([uc, cond]).contiguous() if self._guided else cond.contiguous()
+        self._rep = 2 if (self._guided and not self._split) else 1
         setter = getattr(self.model, "set_context", None)
         if setter is not None:
             setter(self._c_in)   # cross-attention K/V once per prompt batch instead of once per step
@@ -88,19 +94,23 @@ class _SamplerBase:
         if ts is None:
             ts = torch.full((nb,), int(step), device=x2.device, dtype=torch.long)
             self._ts_cache[(int(step), nb)] = ts
-        return self.model.apply_model(x2, ts, self._c_in)
+        return self._exchange(self.model.apply_model(x2, ts, self._c_in))
+
+    def _exchange(self, eps):
+        """-> (eps2, eps_cond): the [uncond; cond] pair, or two pointers when the halves live on two GPUs."""
+        return self.cfg_parallel.exchange(eps) if self._split else (eps, None)
 
     def _step(self, x2, eps2, index, order, hist, b, noise=None, e_out=None, write_x=True):
-        n = x2[0].numel() * b
+        eps2, eps_cond = eps2
         x = x2[:b]
         pred_x0 = torch.empty_like(x)
         x_prev = torch.empty_like(x2) if write_x else None
         xp, p0, e = ops.sampler_step(
-            x, eps2, guided=self._guided, scale=self._scale, order=order, hist=hist, noise=noise,
+            x, eps2, eps_cond=eps_cond, guided=self._guided, scale=self._scale, order=order, hist=hist, noise=noise,
             a_t=float(self.ddim_alphas[index]), a_prev=float(self.ddim_alphas_prev[index]),
             sigma_t=float(self.ddim_sigmas[index]),
             sqrt_one_minus_a_t=float(self.ddim_sqrt_one_minus_alphas[index]),
-            x_prev=x_prev, pred_x0=pred_x0, e_out=e_out, dup=self._guided)
+            x_prev=x_prev, pred_x0=pred_x0, e_out=e_out, dup=self._rep == 2)
         return xp, p0, e
 
     def _blend_mask(self, x2, mask, x0, step, b):
@@ -109,7 +119,7 @@ class _SamplerBase:
         if ts is None:
             ts = self._ts_cache[(int(step), b)] = torch.full((b,), int(step), device=x2.device, dtype=torch.long)
         img_orig = self.model.q_sample(x0, ts)
-        ops.mask_blend(img_orig.contiguous().float(), mask, x2, b, dup=self._guided)
+        ops.mask_blend(img_orig.contiguous().float(), mask, x2, b, dup=self._rep == 2)
 
     @staticmethod
     def _prep_mask(mask, x0, device):
@@ -167,7 +177,7 @@ class PLMSSampler(_SamplerBase):
         img = torch.randn(shape, device=device) if x_T is None else x_T.to(device=device, dtype=torch.float32)
         self._setup_guidance(cond, unconditional_conditioning, unconditional_guidance_scale, b)
         self._ts_cache = {}
-        rep = 2 if self._guided else 1
+        rep = self._rep
         x2 = img.repeat(rep, 1, 1, 1).contiguous() if rep == 2 else img.contiguous().clone()
         time_range = np.flip(self.ddim_timesteps)
         total_steps = time_range.shape[0]
@@ -231,7 +241,7 @@ class DDIMSampler(_SamplerBase):
         mask, x0 = self._prep_mask(mask, x0, img.device)
         self._setup_guidance(cond, uc, scale, b)
         self._ts_cache = {}
-        rep = 2 if self._guided else 1
+        rep = self._rep
         x2 = img.repeat(rep, 1, 1, 1).contiguous() if rep == 2 else img.contiguous().clone()
         time_range = np.flip(timesteps)
         total_steps = time_range.shape[0]
@@ -365,16 +375,16 @@ class DPMSolverSampler(_SamplerBase):
         b = batch_size
         self._setup_guidance(conditioning, unconditional_conditioning, unconditional_guidance_scale, b)
         plan = dpm_solver_plan(self.alphas_cumprod, S)
-        rep = 2 if self._guided else 1
+        rep = self._rep
         x2 = img.repeat(rep, 1, 1, 1).contiguous() if rep == 2 else img.contiguous().clone()
         m_prev = None
         for i, p in enumerate(plan):
             ts = torch.full((x2.shape[0],), p["t_input"], device=device, dtype=torch.float32)
-            eps2 = self.model.apply_model(x2, ts, self._c_in)
+            eps2, eps_cond = self._exchange(self.model.apply_model(x2, ts, self._c_in))
             x2, m_prev = ops.dpm_solver_step(
-                x2[:b], eps2, guided=self._guided, scale=self._scale, sigma_s=p["sigma_s"], alpha_s=p["alpha_s"],
+                x2[:b], eps2, eps_cond=eps_cond, guided=self._guided, scale=self._scale, sigma_s=p["sigma_s"], alpha_s=p["alpha_s"],
                 order=p["order"], m_prev=m_prev, c_x=p["c_x"], c_m=p["c_m"], inv_r0=p["inv_r0"],
-                x_out=torch.empty_like(x2), dup=self._guided)
+                x_out=torch.empty_like(x2), dup=rep == 2)
             if callback:
                 callback(i)
             if img_callback:
