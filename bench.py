@@ -218,6 +218,11 @@ def run_gpu(args):
     clk = clocks.stop() if rank == 0 else None
     step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
+    # sanity of what was timed (outside the timed region): the latent the 51 evaluations produce is finite and the
+    # decoded image is not constant — a NaN anywhere in the UNet would show here
+    lat = pipe(ids_d, un_d, x_T=xT_d, return_latent=True)
+    img_chk = out_h.float()
+    output_ok = bool(torch.isfinite(lat).all()) and float(lat.std()) > 0 and float(img_chk.std()) > 0
 
     # UNet step time (graph replay of one guided evaluation, N_s = 2B), L2 flushed between repetitions
     unet = model.model.diffusion_model
@@ -327,7 +332,7 @@ def run_gpu(args):
                                    "no explicit flush inside a step (UNet-only timing flushes L2)",
                        "arithmetic": "fp16 tensor-core operands, fp32 accumulate / residual stream / norms / softmax",
                        "algorithmic_tflop_per_image": (51 * 2 * UNET_GF_PER_SAMPLE + VAE_DEC_GF + 2 * CLIP_GF_PER_PROMPT) / 1e3},
-            "unet_step_ms": unet_ms, "gpu_launches": int(launches),
+            "unet_step_ms": unet_ms, "gpu_launches": int(launches), "output_finite": output_ok,
             "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(ids_p.nbytes + un_p.nbytes + xT_p.nbytes),
                     "d2h_bytes_per_step": int(out_h.nbytes)},
             "roofline": roof, "cpu_baseline": cpu, "clocks": clk, "larger_batch": extra,
