@@ -122,10 +122,12 @@ def run_reference(args):
     sample = (f"per step: 1 UNet eval N_s=2 @64x64 fp32 ({t_eval:.2f} s); VAE decode 256x256 x4 once ({t_dec:.1f} s); "
               "image time = 51*eval + decode")
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": 0, "steps": args.steps,
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * t_eval, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "txt2img SD-v1-4 random-init, 512x512, 50 PLMS steps, CFG 7.5, batch 1"},
+        "config": {"workload": f"txt2img SD-v1-4 random-init, 512x512, 50 PLMS steps (51 UNet evals), CFG 7.5, "
+                               f"batch {args.batch} per GPU", "parallelism": f"dp{args.gpus}",
+                   "device": f"host CPU, {threads} threads (one image stream; the CPU arm does not scale with --gpus)"},
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
