@@ -440,7 +440,9 @@ class UNetModel(nn.Module):
             g["t"].copy_(timesteps)
             g["graph"].replay()
             ops.add_graph_launches(g["launches"])
-            return g["out"]
+            # a fresh tensor, as the reference returns: callers may keep eps across evaluations (the reference's PLMS
+            # history does when guidance is off, plms.py:159-162), the graph's static output buffer is overwritten
+            return g["out"].clone() if x.dtype == torch.float32 else g["out"].to(x.dtype)
         kvs = self._ctx_kv if key == self._ctx_key else self.context_kv(context)
         t = timesteps.to(torch.float32).contiguous()
         eps = self._forward_impl(x.contiguous().float(), t, kvs)

@@ -94,6 +94,13 @@ def test_unet_cuda_graph_replay_matches_eager(cuda_dev):
         assert rel_l2(b, a) < 1e-5, (step, rel_l2(b, a))
         assert rel_l2(b, sdb_ref(case, sd, x, t, c)) < TOL_TINY
     assert len(graphed._graphs) == 1
+    # graph-mode results are fresh tensors (the static output buffer is not handed out): keeping one across a later
+    # evaluation, as the reference's PLMS history does with guidance off, must not change it
+    t1 = torch.full((x.shape[0],), 981, device=cuda_dev, dtype=torch.long)
+    first = graphed(x, t1, context=c)
+    snap = first.clone()
+    second = graphed(x, torch.full_like(t1, 21), context=c)
+    assert first.data_ptr() != second.data_ptr() and torch.equal(first, snap) and not torch.equal(first, second)
 
 
 def sdb_ref(case, sd, x, t, c):
