@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import CFGS, golden, rel_l2, weights
+from helpers import golden, rel_l2, weights
 from sdb200 import arch
 
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
