@@ -65,3 +65,18 @@ def test_product_path_fails_loudly_without_cuda():
     if not torch.cuda.is_available():
         with pytest.raises(Exception):
             sdb200.ops.cast_f16(torch.zeros(4))
+
+
+def test_integration_doc_struct_matches_header():
+    """The ctypes stub printed in INTEGRATION.md lists the sdb_gemm_desc fields in the header's order (a stale,
+    shorter struct would make the library read past the caller's allocation)."""
+    import os
+    import re
+    from sdb200 import lib as L
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    block = doc[doc.index("class GemmDesc(C.Structure)"):doc.index("lib.sdb_gemm.argtypes")]
+    doc_fields = re.findall(r'\("(\w+)", C\.(\w+)\)', block)
+    import ctypes as C
+    assert [n for n, _ in doc_fields] == [n for n, _ in L.GemmDesc._fields_]
+    assert [C.sizeof(getattr(C, t)) for _, t in doc_fields] == [C.sizeof(t) for _, t in L.GemmDesc._fields_]
