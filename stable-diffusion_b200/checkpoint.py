@@ -83,7 +83,11 @@ def read_state_dict(path):
     """(state_dict, info) from a .safetensors or a pickled .ckpt/.pt/.pth (txt2img.py:51-54)."""
     if str(path).endswith(".safetensors"):
         return read_safetensors(path), {}
-    pl_sd = torch.load(path, map_location="cpu", weights_only=False)
+    try:     # tensors-only unpickling first; full Lightning checkpoints carry extra python objects (callbacks, ...)
+        pl_sd = torch.load(path, map_location="cpu", weights_only=True)
+    except Exception:   # noqa: BLE001 - fall back to the reference's plain torch.load (txt2img.py:51): trusted files only
+        print(f"note: {path} needs full unpickling (not a tensors-only file); load only checkpoints you trust")
+        pl_sd = torch.load(path, map_location="cpu", weights_only=False)
     if isinstance(pl_sd, dict) and "state_dict" in pl_sd:
         return pl_sd["state_dict"], {k: pl_sd[k] for k in ("global_step", "epoch") if k in pl_sd}
     return pl_sd, {}
