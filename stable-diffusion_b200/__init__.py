@@ -7,7 +7,7 @@ __version__ = "0.1.0"
 
 import sys as _sys
 
-from . import arch, checkpoint, clip, diffusion, dist, lib, ops, pipeline, samplers, unet, util, vae  # noqa: E402,F401
+from . import arch, checkpoint, clip, diffusion, dist, lib, ops, pipeline, samplers, tokenizer, unet, util, vae  # noqa: E402,F401
 from .clip import FrozenCLIPEmbedder  # noqa: E402,F401
 from .diffusion import LatentDiffusion  # noqa: E402,F401
 from .samplers import DDIMSampler, DPMSolverSampler, PLMSSampler  # noqa: E402,F401

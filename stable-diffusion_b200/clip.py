@@ -13,6 +13,8 @@ vocabulary in this offline image, so `encode_ids` takes token ids directly (test
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -125,16 +127,29 @@ class FrozenCLIPEmbedder(nn.Module):
         return z.view(B, n, h)
 
     def _tokenize(self, text):
+        """list[str] -> int64 [B, max_length] ids as `modules.py:153-156` (truncation, max_length padding).
+        `version` may be a directory holding vocab.json + merges.txt (host-side BPE in tokenizer.py, no third-party
+        code); otherwise the locally cached transformers tokenizer of that name is used, as the reference does."""
         if self.tokenizer is None:
-            try:
-                from transformers import CLIPTokenizer
-                tok = CLIPTokenizer.from_pretrained(self.version, local_files_only=True)
-                if len(tok) < 49408:  # transformers >= 5 silently builds an empty tokenizer when files are missing
-                    raise FileNotFoundError(f"vocabulary has {len(tok)} entries")
-                self.tokenizer = tok
-            except Exception as e:  # no vocabulary offline
-                raise RuntimeError(f"CLIP tokenizer files for {self.version} are not available offline ({e}); "
-                                   "pass token ids to encode_ids()") from e
+            if os.path.isdir(str(self.version)) and os.path.exists(os.path.join(str(self.version), "vocab.json")):
+                from .tokenizer import CLIPBPETokenizer
+                self.tokenizer = CLIPBPETokenizer.from_dir(str(self.version), self.max_length)
+            else:
+                try:
+                    from transformers import CLIPTokenizer
+                    tok = CLIPTokenizer.from_pretrained(self.version, local_files_only=True)
+                    if len(tok) < 49408:  # transformers >= 5 silently builds an empty tokenizer when files are missing
+                        raise FileNotFoundError(f"vocabulary has {len(tok)} entries")
+                    self.tokenizer = tok
+                except Exception as e:  # no vocabulary offline
+                    raise RuntimeError(f"CLIP tokenizer files for {self.version} are not available offline ({e}); pass "
+                                       "a directory with vocab.json + merges.txt as `version`, or token ids to "
+                                       "encode_ids()") from e
+        if isinstance(text, str):
+            text = [text]
+        from .tokenizer import CLIPBPETokenizer
+        if isinstance(self.tokenizer, CLIPBPETokenizer):
+            return torch.tensor(self.tokenizer(list(text), self.max_length), dtype=torch.long)
         batch = self.tokenizer(text, truncation=True, max_length=self.max_length, return_length=True,
                                return_overflowing_tokens=False, padding="max_length", return_tensors="pt")
         return batch["input_ids"]
