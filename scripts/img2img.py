@@ -42,6 +42,8 @@ def main():
     p.add_argument("--config", type=str, default="configs/stable-diffusion/v1-inference.yaml")
     p.add_argument("--ckpt", type=str, default="models/ldm/stable-diffusion-v1/model.ckpt")
     p.add_argument("--seed", type=int, default=42)
+    p.add_argument("--clip_vocab", type=str, default=None,
+                   help="directory with the CLIP vocab.json + merges.txt (host-side BPE); default: transformers' local cache")
     p.add_argument("--size", type=int, default=512, help="side of the synthetic init image when --init-img is omitted")
     opt = p.parse_args()
     torch.manual_seed(opt.seed)
@@ -53,9 +55,17 @@ def main():
         init = load_img(opt.init_img).to(device).repeat(B, 1, 1, 1)
     else:
         init = (torch.rand(B, 3, opt.size, opt.size, device=device) * 2 - 1)
-    ids = synthetic_ids(B, 1234, device)
-    un = torch.full((B, 77), 49407, dtype=torch.long, device=device)
-    un[:, 0] = 49406
+    enc = model.cond_stage_model
+    if opt.clip_vocab:
+        enc.version, enc.tokenizer = opt.clip_vocab, None
+    try:
+        ids = enc._tokenize(B * [opt.prompt]).to(device)
+        un = enc._tokenize(B * [""]).to(device)
+    except RuntimeError as e:
+        print(f"tokenizer unavailable ({e}); using seeded token ids")
+        ids = synthetic_ids(B, 1234, device)
+        un = torch.full((B, 77), 49407, dtype=torch.long, device=device)
+        un[:, 0] = 49406
     os.makedirs(opt.outdir, exist_ok=True)
     tic = time.time()
     for n in range(opt.n_iter):

@@ -64,6 +64,8 @@ def main():
     p.add_argument("--ckpt", type=str, default="models/ldm/stable-diffusion-v1/model.ckpt")
     p.add_argument("--seed", type=int, default=42)
     p.add_argument("--precision", type=str, choices=["full", "autocast"], default="autocast")
+    p.add_argument("--clip_vocab", type=str, default=None,
+                   help="directory with the CLIP vocab.json + merges.txt (host-side BPE); default: transformers' local cache")
     p.add_argument("--token_seed", type=int, default=1234, help="seed of the stand-in token ids (no tokenizer offline)")
     opt = p.parse_args()
     if opt.laion400m:
@@ -71,7 +73,8 @@ def main():
     torch.manual_seed(opt.seed)           # seed_everything (txt2img.py:243)
     device = torch.device("cuda")
     model = load_model_from_config(opt.config, opt.ckpt, device)
-    pipe = pipeline.Txt2Img(model, sampler="dpm_solver" if opt.dpm_solver else ("plms" if opt.plms else "ddim"), steps=opt.ddim_steps, scale=opt.scale,
+    sampler = "dpm_solver" if opt.dpm_solver else ("plms" if opt.plms else "ddim")
+    pipe = pipeline.Txt2Img(model, sampler=sampler, steps=opt.ddim_steps, scale=opt.scale,
                             height=opt.H, width=opt.W, eta=opt.ddim_eta, f=opt.f, channels=opt.C)
     os.makedirs(opt.outdir, exist_ok=True)
     sample_path = os.path.join(opt.outdir, "samples")
@@ -83,6 +86,8 @@ def main():
     else:
         prompts = [opt.prompt]
     enc = model.cond_stage_model
+    if opt.clip_vocab:
+        enc.version, enc.tokenizer = opt.clip_vocab, None
     start_code = torch.randn([B, opt.C, opt.H // opt.f, opt.W // opt.f], device=device) if opt.fixed_code else None
     base_count = len(os.listdir(sample_path))
     tic = time.time()
