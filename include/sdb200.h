@@ -24,6 +24,10 @@ const char* sdb_last_error(void);
 int sdb_version(void);
 int sdb_sm_count(void);
 long long sdb_launch_count(void); /* kernels launched through this library since load */
+/* Debug only: subsequent sdb_gemm launches write per-CTA phase timestamps (8-word launch header + 8 words per CTA,
+ * 1288 words per launch) into the device buffer `buf` of n_words uint64; NULL switches tracing off. Returns the
+ * number of words handed out since the previous call. Used by scripts/timeline_unet.py. */
+long long sdb_debug_trace(void* buf, int64_t n_words);
 
 /* ---- epilogue activations ---- */
 enum {

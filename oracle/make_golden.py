@@ -249,6 +249,54 @@ def clip_goldens():
     save("clip.pt", cases)
 
 
+def _sub(t, stride=4, off=1):
+    """Strided pixel subset of an NCHW image (full-size decodes are megabytes; rel-L2 over a regular 1/16 sample of the
+    pixels plus the whole-tensor norm pins the same arithmetic)."""
+    return t[..., off::stride, off::stride].contiguous()
+
+
+@torch.no_grad()
+def fullsize_goldens():
+    """BASELINE-size fixtures from the UNMODIFIED reference: SD-v1 UNet at the C5 latent
+    (2,4,96,96), C1 (2,4,64,64) with a SECOND weight seed, and the SD-v1 VAE at the sizes the benchmarks decode /
+    encode (64x64 -> 512^2 and 96x96 -> 768^2). Inputs are regenerated from the stored seeds by the tests."""
+    out = dict(unet=[], vae=[])
+    cfg = arch.SD_V1_UNET
+    for wseed, xs, ts, xseed in ((UNET_SEED, (2, 4, 96, 96), [981, 981], 110), (21, (2, 4, 64, 64), [501, 21], 111)):
+        sd = arch.random_state_dict(arch.unet_param_shapes(cfg), wseed)
+        net = R.build_unet(cfg)
+        net.load_state_dict(sd, strict=True)
+        x = gen(xs, xseed)
+        t = torch.tensor(ts, dtype=torch.long)
+        ctx = gen((xs[0], 77, cfg["context_dim"]), xseed + 100)
+        t0 = time.time()
+        eps = net(x, t, context=ctx)
+        dt = time.time() - t0
+        mine = O.unet_forward(sd, x, t, ctx, num_heads=cfg["num_heads"])
+        print(f"unet sdv1 seed {wseed} {xs} t={ts}: ref {dt:.1f}s eps std {float(eps.std()):.3f}  oracle rel-L2 {rel(mine, eps):.2e}")
+        out["unet"].append(dict(cfg="sdv1", seed=wseed, x_shape=xs, x_seed=xseed, ctx_seed=xseed + 100, t=t, eps=eps))
+        del net, sd
+    vcfg = arch.SD_V1_VAE
+    sd = arch.random_state_dict(arch.vae_param_shapes(vcfg), VAE_SEED)
+    vae = R.build_vae(vcfg)
+    vae.load_state_dict(sd, strict=True)
+    for lat, zseed in ((64, 310), (96, 311)):
+        z = gen((1, 4, lat, lat), zseed)
+        img = gen((1, 3, 8 * lat, 8 * lat), zseed + 10).clamp(-1, 1)
+        t0 = time.time()
+        dec = vae.decode(z)
+        raw_moments = vae.quant_conv(vae.encoder(img))
+        dt = time.time() - t0
+        o_dec = O.vae_decode(sd, z)
+        o_mom = O.vae_encode_moments(sd, img)
+        print(f"vae sdv1 latent {lat}: ref {dt:.1f}s; decode oracle rel {rel(o_dec, dec):.2e}; encode oracle rel "
+              f"{rel(o_mom, raw_moments):.2e}; dec std {float(dec.std()):.3f}")
+        out["vae"].append(dict(cfg="sdv1", seed=VAE_SEED, latent=lat, z_seed=zseed, img_seed=zseed + 10,
+                               dec_sub=_sub(dec), dec_norm=float(dec.double().norm()), dec_mean=float(dec.double().mean()),
+                               dec_crop=dec[..., 100:164, 200:264].contiguous(), moments=raw_moments))
+    save("fullsize.pt", out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -263,3 +311,5 @@ if __name__ == "__main__":
         clip_goldens()
     if "samplers_ext" in which:
         samplers_ext_goldens()
+    if "fullsize" in which:   # slow (minutes, ~20 GB of host memory): not part of the default set
+        fullsize_goldens()

@@ -428,3 +428,8 @@ extern "C" const char* sdb_last_error(void) { return sdb::last_error(); }
 extern "C" int sdb_version(void) { return 100; }
 extern "C" int sdb_sm_count(void) { return sdb::sm_count(); }
 extern "C" long long sdb_launch_count(void) { return sdb::launch_count(); }
+extern "C" long long sdb_debug_trace(void* buf, int64_t n_words) {
+  long long used = sdb::trace_used();
+  sdb::set_trace(buf, n_words);
+  return used;
+}

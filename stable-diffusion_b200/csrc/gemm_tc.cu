@@ -70,6 +70,7 @@ struct GemmArgs {
   int b_static;     // B is a weight matrix: safe to prefetch before griddepcontrol.wait
   int fast;         // outputs go through the TMA-store epilogue
   int bw, bh;       // store box: bw x bh x (32 / (bw*bh)) output pixels per epilogue warp
+  unsigned long long* trace;  // debug: per-CTA phase timestamps (sdb_debug_trace), NULL in production
 };
 
 // Exact-erf GELU (attention.py:44, F.gelu default) with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far
@@ -194,6 +195,17 @@ __device__ __forceinline__ void drain_chunk(const GemmArgs& p, const float* stag
   }
 }
 
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// debug trace: word w of this CTA's record (8 words per CTA after an 8-word launch header)
+#define SDB_TR(w, val)                                                          \
+  do {                                                                          \
+    if (p.trace) p.trace[8 + blockIdx.x * 8 + (w)] = (val);                     \
+  } while (0)
+
 template <int BN>
 struct GemmCfg {
   static constexpr int STAGES = BN <= 32 ? 6 : BN <= 64 ? 6 : BN <= 128 ? 4 : BN <= 160 ? 4 : 3;
@@ -225,6 +237,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   const int lane = threadIdx.x & 31;
   const int tiles_total = p.m_tiles * p.n_tiles * p.splits;
   pdl_launch_dependents();   // the next kernel may start its prologue while this one runs
+  const long long clk0 = clock64();
+  if (p.trace && threadIdx.x == 0) {
+    SDB_TR(0, gtimer());
+    if (blockIdx.x == 0) {
+      p.trace[0] = gridDim.x;
+      p.trace[1] = BN;
+      p.trace[2] = p.splits;
+      p.trace[3] = p.k_iters;
+      p.trace[4] = p.M;
+      p.trace[5] = p.N;
+      p.trace[6] = p.taps;
+      p.trace[7] = tiles_total;
+    }
+  }
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < p.nsrc; ++i) tma_prefetch_desc(&tm.a[i]);
@@ -253,6 +279,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = tmem_base_smem;
+  if (threadIdx.x == 0) SDB_TR(2, clock64() - clk0);
 
   if (warp == 0) {
     if (elect_one()) {
@@ -273,6 +300,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         }
       }
       pdl_wait();
+      SDB_TR(3, clock64() - clk0);
       for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
         const int m_tile = tile % p.m_tiles;
         const int rest = tile / p.m_tiles;
@@ -331,6 +359,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           const uint32_t ph = (i / STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
+          if (i == 0) SDB_TR(4, clock64() - clk0);
           const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
           const uint64_t da = umma_desc_k128(a_addr);
           const uint64_t db = umma_desc_k128(a_addr + A_BYTES);
@@ -343,6 +372,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         }
         umma_commit(&acc_full[ab]);
       }
+      SDB_TR(5, clock64() - clk0);
     }
   } else {
     // epilogue warps 2..9 : TMEM lane group = warp % 4; the two warps of a lane group alternate chunks
@@ -387,6 +417,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       }
       mbar_wait(&acc_full[ab], (local >> 1) & 1);
       tc_fence_after();
+      if (local == 0 && threadIdx.x == 64) SDB_TR(6, clock64() - clk0);
       const uint32_t taddr = tmem_d + ab * BN + (static_cast<uint32_t>(lg * 32) << 16);
       int last_c = -1;
       for (int c = par; c < n_chunks; c += 2) last_c = c;
@@ -600,12 +631,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     // smem may be released once the bulk stores have READ it; their global writes complete with the grid
     if (lane == 0) tma_store_wait_read<0>();
     tc_fence_before();
+    if (threadIdx.x == 64) SDB_TR(7, clock64() - clk0);
   }
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_d, TMEM_COLS);
   }
+  if (threadIdx.x == 0) SDB_TR(1, gtimer());
 }
 
 // split-K second pass: sum the fp32 partial planes and apply the fused epilogue. Block = 32 rows x 128 columns
@@ -961,6 +994,7 @@ extern "C" int sdb_gemm(const sdb_gemm_desc* d, sdb_stream_t stream) {
       SDB_CUDA(cudaMemsetAsync(p.stats, 0, static_cast<size_t>(STAT_SLOTS) * p.n_samples * d->n * 2 * sizeof(double), st));
   }
 
+  p.trace = trace_slot(8 + 8 * 160);
   int rc;
   switch (bn) {
     case 32: rc = launch_gemm<32>(tm, p, st); break;

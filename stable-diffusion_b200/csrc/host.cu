@@ -80,6 +80,21 @@ bool pdl_enabled() {
   return v == 1;
 }
 
+static unsigned long long* g_trace = nullptr;
+static long long g_trace_words = 0, g_trace_used = 0;
+void set_trace(void* buf, long long n_words) {
+  g_trace = static_cast<unsigned long long*>(buf);
+  g_trace_words = buf ? n_words : 0;
+  g_trace_used = 0;
+}
+long long trace_used() { return g_trace_used; }
+unsigned long long* trace_slot(int n_words) {
+  if (!g_trace || g_trace_used + n_words > g_trace_words) return nullptr;
+  unsigned long long* p = g_trace + g_trace_used;
+  g_trace_used += n_words;
+  return p;
+}
+
 static long long g_launches = 0;
 void count_launch() { ++g_launches; }
 long long launch_count() { return g_launches; }

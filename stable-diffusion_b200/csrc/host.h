@@ -37,6 +37,11 @@ int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int swizzle_by
 
 int sm_count();
 
+// debug phase tracing (sdb_debug_trace): next n-word slot of the trace buffer, or nullptr when tracing is off / full
+unsigned long long* trace_slot(int n_words);
+void set_trace(void* buf, long long n_words);
+long long trace_used();
+
 // kernels launched through the C ABI since load (bench.py's gpu_launches)
 void count_launch();
 long long launch_count();

@@ -63,6 +63,7 @@ SIGNATURES = {
     "sdb_version": ([], C.c_int),
     "sdb_sm_count": ([], C.c_int),
     "sdb_launch_count": ([], C.c_longlong),
+    "sdb_debug_trace": ([_P, _L], C.c_longlong),
     "sdb_gemm": ([C.POINTER(GemmDesc), _P], C.c_int),
     "sdb_attention": ([C.POINTER(AttnDesc), _P], C.c_int),
     "sdb_groupnorm": ([_P, _P, _I, _I, _I, _I, _I, _P, _P, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P], C.c_int),

@@ -100,3 +100,19 @@ def test_samplers_oracle_50_steps_and_img2img():
     z_dec = O.ddim_sample(model_fn, z_enc, g["c"], g["uc"], 5.0, S=50, t_start=g["t_enc"])
     assert rel_l2(z_dec, g["z_dec"]) < 1e-4
     assert rel_l2(O.decode_first_stage(vsd, z_dec), g["x_dec"]) < 1e-4
+
+
+def test_oracle_matches_reference_fullsize_fixtures():
+    """BASELINE-size fixtures (tests/golden/fullsize.pt, written by the unmodified reference): the oracle reproduces the
+    second-weight-seed C1 eps bit-exactly and the 512^2 VAE decode to fp32 round-off (the 96x96 cases need ~20 GB and
+    half a minute each; make_golden.py prints their oracle error when the fixtures are made)."""
+    import ldm_oracle as O
+    fs = golden("fullsize.pt")
+    case = fs["unet"][1]
+    g = lambda shape, seed: torch.randn(shape, generator=torch.Generator().manual_seed(seed))
+    x, ctx = g(case["x_shape"], case["x_seed"]), g((case["x_shape"][0], 77, 768), case["ctx_seed"])
+    eps = O.unet_forward(weights("unet", "sdv1", case["seed"]), x, case["t"], ctx)
+    assert torch.equal(eps, case["eps"])
+    v = fs["vae"][0]
+    dec = O.vae_decode(weights("vae", "sdv1", v["seed"]), g((1, 4, v["latent"], v["latent"]), v["z_seed"]))
+    assert rel_l2(dec[..., 1::4, 1::4], v["dec_sub"]) < 5e-6 and abs(float(dec.double().norm()) / v["dec_norm"] - 1) < 1e-6
