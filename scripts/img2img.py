@@ -42,13 +42,15 @@ def main():
     p.add_argument("--config", type=str, default="configs/stable-diffusion/v1-inference.yaml")
     p.add_argument("--ckpt", type=str, default="models/ldm/stable-diffusion-v1/model.ckpt")
     p.add_argument("--seed", type=int, default=42)
+    p.add_argument("--random_init", action="store_true", help="seeded random weights instead of a checkpoint")
+    p.add_argument("--unsafe-ckpt", action="store_true", help="allow full unpickling of a .ckpt (runs code from the file)")
     p.add_argument("--clip_vocab", type=str, default=None,
                    help="directory with the CLIP vocab.json + merges.txt (host-side BPE); default: transformers' local cache")
     p.add_argument("--size", type=int, default=512, help="side of the synthetic init image when --init-img is omitted")
     opt = p.parse_args()
     torch.manual_seed(opt.seed)
     device = torch.device("cuda")
-    model = load_model_from_config(opt.config, opt.ckpt, device)
+    model = load_model_from_config(opt.config, opt.ckpt, device, random_init=opt.random_init, unsafe_ckpt=opt.unsafe_ckpt)
     pipe = pipeline.Img2Img(model, steps=opt.ddim_steps, scale=opt.scale, strength=opt.strength, eta=opt.ddim_eta)
     B = opt.n_samples
     if opt.init_img:

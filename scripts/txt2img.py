@@ -3,7 +3,7 @@
 
   python scripts/txt2img.py --prompt "a photograph of an astronaut riding a horse" --plms --ckpt sd-v1-4.ckpt
 
-Without --ckpt the three stages get seeded random weights (no checkpoint ships offline); without the CLIP vocabulary
+With --random_init the three stages get seeded random weights (no checkpoint ships offline); without the CLIP vocabulary
 files the prompt is replaced by seeded token ids (--token_seed). The safety checker and the invisible watermark of the
 reference script are third-party post-processing outside the denoising path and are not applied.
 """
@@ -19,16 +19,26 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import sdb200  # noqa: E402
 from sdb200 import pipeline  # noqa: E402
 
+DEFAULT_CONFIG = "configs/stable-diffusion/v1-inference.yaml"
 
-def load_model_from_config(config, ckpt, device, verbose=False):
-    """scripts/txt2img.py:49-66 via sdb200.checkpoint (pickled .ckpt or .safetensors, reference YAML or built-in v1)."""
-    if ckpt and os.path.exists(ckpt):
-        cfg = config if (config and os.path.exists(config)) else {"model": pipeline.v1_model_config()}
-        return sdb200.checkpoint.load_model_from_config(cfg, ckpt, device=device, verbose=verbose)
-    print("no checkpoint given: seeded random-init weights (images will be noise-like)")
-    model = pipeline.build_model()
-    pipeline.load_random_weights(model, device, gen_device=device)
-    return model.eval()
+
+def load_model_from_config(config, ckpt, device, verbose=False, random_init=False, unsafe_ckpt=False):
+    """scripts/txt2img.py:49-66 via sdb200.checkpoint (pickled .ckpt or .safetensors, reference YAML or built-in v1).
+    Seeded random weights are used only on request (--random_init): a missing checkpoint or config path is an error."""
+    if config and not os.path.exists(config):
+        if config != DEFAULT_CONFIG:
+            raise FileNotFoundError(f"--config {config} does not exist")
+        config = None                         # the reference's default path is absent here: built-in v1-inference values
+    if random_init:
+        print("--random_init: seeded random-init weights (images will be noise-like)")
+        model = pipeline.build_model()
+        pipeline.load_random_weights(model, device, gen_device=device)
+        return model.eval()
+    if not ckpt or not os.path.exists(ckpt):
+        raise FileNotFoundError(f"checkpoint {ckpt!r} does not exist (pass --ckpt, or --random_init for seeded random "
+                                "weights)")
+    cfg = config if config else {"model": pipeline.v1_model_config()}
+    return sdb200.checkpoint.load_model_from_config(cfg, ckpt, device=device, verbose=verbose, allow_pickle=unsafe_ckpt)
 
 
 def synthetic_ids(n, seed, device):
@@ -60,9 +70,11 @@ def main():
     p.add_argument("--n_rows", type=int, default=0)
     p.add_argument("--scale", type=float, default=7.5)
     p.add_argument("--from-file", type=str)
-    p.add_argument("--config", type=str, default="configs/stable-diffusion/v1-inference.yaml")
+    p.add_argument("--config", type=str, default=DEFAULT_CONFIG)
     p.add_argument("--ckpt", type=str, default="models/ldm/stable-diffusion-v1/model.ckpt")
     p.add_argument("--seed", type=int, default=42)
+    p.add_argument("--random_init", action="store_true", help="seeded random weights instead of a checkpoint")
+    p.add_argument("--unsafe-ckpt", action="store_true", help="allow full unpickling of a .ckpt (runs code from the file)")
     p.add_argument("--precision", type=str, choices=["full", "autocast"], default="autocast")
     p.add_argument("--clip_vocab", type=str, default=None,
                    help="directory with the CLIP vocab.json + merges.txt (host-side BPE); default: transformers' local cache")
@@ -72,7 +84,7 @@ def main():
         raise NotImplementedError("--laion400m (a different checkpoint/config) is outside the SD-v1 path of this engine")
     torch.manual_seed(opt.seed)           # seed_everything (txt2img.py:243)
     device = torch.device("cuda")
-    model = load_model_from_config(opt.config, opt.ckpt, device)
+    model = load_model_from_config(opt.config, opt.ckpt, device, random_init=opt.random_init, unsafe_ckpt=opt.unsafe_ckpt)
     sampler = "dpm_solver" if opt.dpm_solver else ("plms" if opt.plms else "ddim")
     pipe = pipeline.Txt2Img(model, sampler=sampler, steps=opt.ddim_steps, scale=opt.scale,
                             height=opt.H, width=opt.W, eta=opt.ddim_eta, f=opt.f, channels=opt.C)

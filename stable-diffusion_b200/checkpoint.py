@@ -79,14 +79,23 @@ def write_safetensors(path, tensors, metadata=None):
             f.write(b)
 
 
-def read_state_dict(path):
-    """(state_dict, info) from a .safetensors or a pickled .ckpt/.pt/.pth (txt2img.py:51-54)."""
+def read_state_dict(path, allow_pickle=False):
+    """(state_dict, info) from a .safetensors or a pickled .ckpt/.pt/.pth (txt2img.py:51-54).
+
+    Pickled files are read with tensors-only unpickling (plus the few plain containers a Lightning checkpoint
+    carries). Full unpickling executes arbitrary code from the file, so — unlike the reference's bare `torch.load` —
+    it is an explicit opt-in: allow_pickle=True (CLI: --unsafe-ckpt), for files you trust."""
     if str(path).endswith(".safetensors"):
         return read_safetensors(path), {}
-    try:     # tensors-only unpickling first; full Lightning checkpoints carry extra python objects (callbacks, ...)
+    try:
         pl_sd = torch.load(path, map_location="cpu", weights_only=True)
-    except Exception:   # noqa: BLE001 - fall back to the reference's plain torch.load (txt2img.py:51): trusted files only
-        print(f"note: {path} needs full unpickling (not a tensors-only file); load only checkpoints you trust")
+    except Exception as ex:   # noqa: BLE001
+        if not allow_pickle:
+            raise RuntimeError(
+                f"{path} is not a tensors-only checkpoint ({type(ex).__name__}: {str(ex).splitlines()[0][:200]}). "
+                "Full unpickling runs code from the file: pass allow_pickle=True / --unsafe-ckpt if you trust it, or "
+                "convert it once with sdb200.checkpoint.write_safetensors.") from ex
+        print(f"note: {path} is being fully unpickled (allow_pickle=True); load only checkpoints you trust")
         pl_sd = torch.load(path, map_location="cpu", weights_only=False)
     if isinstance(pl_sd, dict) and "state_dict" in pl_sd:
         return pl_sd["state_dict"], {k: pl_sd[k] for k in ("global_step", "epoch") if k in pl_sd}
@@ -111,13 +120,13 @@ def load_config(config):
     return node
 
 
-def load_model_from_config(config, ckpt, device="cuda", verbose=False):
+def load_model_from_config(config, ckpt, device="cuda", verbose=False, allow_pickle=False):
     """scripts/txt2img.py:49-66. Returns the model in eval mode on `device` (device=None: leave it on the host with the
     tensors adopted; `.cuda()` packs them later). Missing / unexpected keys are printed when verbose, as the
     reference does; EMA copies (`model_ema.*`) and training-only buffers in a full checkpoint are simply unexpected."""
     node = load_config(config)
     print(f"Loading model from {ckpt}")
-    sd, info = read_state_dict(ckpt)
+    sd, info = read_state_dict(ckpt, allow_pickle=allow_pickle)
     if "global_step" in info:
         print(f"Global Step: {info['global_step']}")
     model = instantiate_from_config(remap_config(node))

@@ -109,7 +109,8 @@ class UNetModel(nn.Module):
         self.shapes = unet_param_shapes(self.cfg)
         self.precision = self.PRECISION
         self.W = None           # packed weights (device)
-        self._ctx_key = None
+        self._ctx_ref = None    # the context tensor whose cross-attention K/V are cached (strong reference)
+        self._ctx_ver = -1
         self._ctx_kv = None
         self._kv_static = {}
         self._graphs = {}
@@ -223,7 +224,7 @@ class UNetModel(nn.Module):
         W["emb_b"] = torch.cat(emb_b, 0).float().contiguous()
         W["st_list"] = [p for grp in W["input"] + [W["middle"]] + W["output"] for k, p in grp if k == "st"]
         self.W = W
-        self._ctx_key = None
+        self._ctx_ref = None
         self._kv_static = {}
         self._graphs = {}
 
@@ -327,11 +328,23 @@ class UNetModel(nn.Module):
         return out
 
     def set_context(self, context):
-        """Cache the cross-attention K/V for `context` ([uncond; cond] batch); forward() reuses it while the same
-        tensor (same storage, same version) is passed."""
+        """Cache the cross-attention K/V for `context` ([uncond; cond] batch). forward() reuses them for the same
+        tensor object (unmodified since) or for a tensor with equal contents; the cached tensor is kept alive, so a new
+        prompt can never alias it through a recycled allocation."""
         self._ctx_kv = self.context_kv(context, static=True)
-        self._ctx_key = (context.data_ptr(), context._version, tuple(context.shape))
+        self._ctx_ref, self._ctx_ver = context, context._version
         return self._ctx_kv
+
+    def _context_cached(self, context):
+        ref = self._ctx_ref
+        if ref is None or self._ctx_kv is None:
+            return False
+        if context is ref:
+            return context._version == self._ctx_ver
+        # a different tensor object (the reference samplers build torch.cat([uc, c]) every step, plms.py:182-185):
+        # compare contents - a 2x77x768 compare is far cheaper than 32 projection GEMMs
+        return (ref._version == self._ctx_ver and context.shape == ref.shape and context.dtype == ref.dtype
+                and context.device == ref.device and bool(torch.equal(context, ref)))
 
     def _run_layers(self, layers, h, skip, film, kvs, st_idx):
         for kind, p in layers:
@@ -429,9 +442,9 @@ class UNetModel(nn.Module):
         nb, _, H, Wd = x.shape
         lv = len(self.cfg["channel_mult"]) - 1
         assert H % (1 << lv) == 0 and Wd % (1 << lv) == 0, "latent size must be divisible by 2^(levels-1)"
-        key = (context.data_ptr(), context._version, tuple(context.shape))
+        cached = self._context_cached(context)
         if self.use_cuda_graph:
-            if key != self._ctx_key:
+            if not cached:
                 self.set_context(context)
             g = self._graph_for(tuple(x.shape), self._ctx_kv)
             assert g["kvs"] is self._ctx_kv or all(a[0].data_ptr() == b[0].data_ptr() for a, b in zip(g["kvs"], self._ctx_kv))
@@ -443,7 +456,7 @@ class UNetModel(nn.Module):
             # a fresh tensor, as the reference returns: callers may keep eps across evaluations (the reference's PLMS
             # history does when guidance is off, plms.py:159-162), the graph's static output buffer is overwritten
             return g["out"].clone() if x.dtype == torch.float32 else g["out"].to(x.dtype)
-        kvs = self._ctx_kv if key == self._ctx_key else self.context_kv(context)
+        kvs = self._ctx_kv if cached else self.context_kv(context)
         t = timesteps.to(torch.float32).contiguous()
         eps = self._forward_impl(x.contiguous().float(), t, kvs)
         return eps.to(x.dtype)

@@ -109,3 +109,20 @@ def test_load_model_from_config_errors(tmp_path):
         checkpoint.load_model_from_config(cfg, path, device=None)
     with pytest.raises(KeyError):
         checkpoint.load_config({"model": {"params": {}}})
+
+
+def test_pickled_checkpoint_with_code_is_refused_unless_opted_in(tmp_path):
+    """A .ckpt that needs full unpickling (it would execute code from the file) raises by default; only
+    allow_pickle=True falls back to the reference's plain torch.load (txt2img.py:51)."""
+    from sdb200 import checkpoint
+
+    class Payload:                       # stands in for the arbitrary python objects of a Lightning checkpoint
+        def __reduce__(self):
+            return (dict, ((("marker", 1),),))
+
+    path = str(tmp_path / "full.ckpt")
+    torch.save({"state_dict": {"w": torch.ones(2)}, "callbacks": Payload()}, path)
+    with pytest.raises(RuntimeError, match="allow_pickle"):
+        checkpoint.read_state_dict(path)
+    sd, _ = checkpoint.read_state_dict(path, allow_pickle=True)
+    assert torch.equal(sd["w"], torch.ones(2))

@@ -106,3 +106,24 @@ def test_unet_cuda_graph_replay_matches_eager(cuda_dev):
 def sdb_ref(case, sd, x, t, c):
     import ldm_oracle as O
     return O.unet_forward(sd, x.cpu(), t.cpu(), c.cpu(), num_heads=CFGS["unet"][case["cfg"]]["num_heads"])
+
+
+def test_unet_context_cache_is_not_fooled_by_a_recycled_allocation(cuda_dev):
+    """A new prompt's context that lands at the address of the previous (freed) one, same shape and version 0, must not
+    reuse the cached cross-attention K/V; an equal-valued copy may."""
+    case = golden("unet.pt")[0]
+    m = _model(case["cfg"], case["seed"], cuda_dev)
+    x, t = case["x"].to(cuda_dev), case["t"].to(cuda_dev)
+    g = torch.Generator().manual_seed(5)
+    ctx_a = torch.randn(case["ctx"].shape, generator=g)
+    ctx_b = torch.randn(case["ctx"].shape, generator=g)
+    a_dev = ctx_a.to(cuda_dev)
+    m.set_context(a_dev)
+    ref_a = m(x, t, context=a_dev).clone()
+    del a_dev
+    b_dev = ctx_b.to(cuda_dev)                  # typically the caching allocator hands back the same block
+    out_b = m(x, t, context=b_dev).clone()
+    ref_b = sdb_ref(case, weights("unet", case["cfg"], case["seed"]), x, t, b_dev)
+    assert rel_l2(out_b, ref_b) < TOL_TINY and rel_l2(out_b, ref_a) > 1e-2
+    out_a2 = m(x, t, context=ctx_a.to(cuda_dev))   # equal contents, different object: served from the cache or not, same eps
+    assert rel_l2(out_a2, ref_a) < 1e-4
