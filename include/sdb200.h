@@ -85,6 +85,11 @@ typedef struct sdb_gemm_desc {
   int32_t stats_prezeroed; /* non-zero: the caller already zeroed stats_out (one arena memset per forward pass) */
   int32_t b_dynamic;       /* non-zero: b is an activation produced by the preceding kernel (e.g. V^T = W_v . X^T swaps
                               the operand roles), so it must not be prefetched ahead of the programmatic-launch wait */
+  int32_t conv_stride;     /* taps = 9 only. 0/1: stride 1. 2: stride-2 conv read straight from the NHWC input through
+                              strided TMA boxes (no im2col): Downsample, openaimodel.py:149-153; model.py:72-76 */
+  int32_t conv_shift;      /* input pixel of output o, tap t (per axis) = stride*o + t - 1 + conv_shift: 0 = zero pad 1
+                              on every side (UNet), 1 = pad only right/bottom (the VAE's asymmetric F.pad, model.py:73) */
+  int32_t in_h, in_w;      /* input height / width when they differ from the output's h / w (stride 2); 0 = h, w */
 } sdb_gemm_desc;
 
 int sdb_gemm(const sdb_gemm_desc* d, sdb_stream_t stream);

@@ -70,6 +70,9 @@ struct GemmArgs {
   int b_static;     // B is a weight matrix: safe to prefetch before griddepcontrol.wait
   int fast;         // outputs go through the TMA-store epilogue
   int bw, bh;       // store box: bw x bh x (32 / (bw*bh)) output pixels per epilogue warp
+  int cstride, cshift;   // 3x3 conv: input pixel = cstride * o + tap - 1 + cshift (per axis)
+  int film_table;   // 1: rows 0-63 / 64-127 of every tile belong to one sample each, so bias + FiLM fold into a
+                    // per-tile shared-memory column table; 0: FiLM is read per row from global memory
   unsigned long long* trace;  // debug: per-CTA phase timestamps (sdb_debug_trace), NULL in production
 };
 
@@ -232,6 +235,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   // fused GroupNorm statistics: [lane group][column][sum, sum of squares]; one writer per slot per tile and a
   // fixed-order fold at the flush (deterministic; the cross-CTA combine uses fp64 atomics)
   __shared__ float colsum[4 * BN * 2];
+  // per-tile column constants of the fused epilogue: bias[col] (+ FiLM[sample of the row half][col]), so the chunk
+  // loop reads them from shared memory instead of paying a global-load latency per chunk
+  __shared__ __align__(16) float coltab[2 * BN];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -337,7 +343,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           int src = 0;
           while (src + 1 < p.nsrc && cc >= p.cb[src + 1]) ++src;
           uint8_t* a_s = smem + s * STAGE_BYTES;
-          tma_load_4d(a_s, &tm.a[src], &full_bar[s], (cc - p.cb[src]) * BK, x0 + dx, y0 + dy, n0);
+          tma_load_4d(a_s, &tm.a[src], &full_bar[s], (cc - p.cb[src]) * BK, x0 * p.cstride + dx + p.cshift,
+                      y0 * p.cstride + dy + p.cshift, n0);
           if (!prefetched) tma_load_2d(a_s + A_BYTES, &tm.b, &full_bar[s], it * BK, n_tile * BN);
         }
       }
@@ -375,20 +382,29 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       SDB_TR(5, clock64() - clk0);
     }
   } else {
-    // epilogue warps 2..9 : TMEM lane group = warp % 4; the two warps of a lane group alternate chunks
+    // epilogue warps 2..9 : TMEM lane group = warp % 4; the two warps of a lane group alternate chunks.
+    // Latency plan: everything the fused epilogue reads from global memory is requested BEFORE the accumulator is
+    // ready - bias (+ FiLM) of the tile's columns go to a shared-memory table, the residual rows of a chunk are
+    // prefetched into registers one chunk ahead (the first one while the main loop still runs) - so the chunk loop is
+    // TMEM load -> FMAs -> staging -> TMA store with no exposed L2 round trip.
     pdl_wait();   // residual / FiLM reads and all output writes come after the previous kernel has completed
     const int ew = warp - 2;
     const int lg = warp & 3;
     const int par = ew >> 2;
+    const int et = threadIdx.x - 64;
     uint8_t* stg = staging + ew * STG_WARP_BYTES;
     float* stage = reinterpret_cast<float*>(stg);  // scalar path: [32][33] floats
     const bool geglu = (p.act == SDB_ACT_GEGLU) && !p.ws;
     constexpr int HALF = BN / 2;
     const int n_chunks = geglu ? HALF / 32 : BN / 32;
+    const int n_lim = geglu ? p.N / 2 : p.N;   // output columns that exist
     const bool st32 = p.ws || p.out_f32;   // an fp32 tile is staged in some phase (output or split-K partial)
     const bool st16 = p.out_f16 != nullptr;
     // staging buffers per chunk parity: fp32 tiles 4 KB each; fp16 hi 2 KB + lo 2 KB each (fp32+fp16 together: single)
     const bool dbl = !(st32 && st16);
+    const bool split_fast = p.ws && p.fast;   // raw fp32 partial planes; finished by splitk_epilogue_kernel
+    const bool use_tab = p.fast && !split_fast;
+    const bool pre_res = use_tab && !geglu && p.residual != nullptr;
     uint32_t flip = 0;
     uint32_t local = 0;
     for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x, ++local) {
@@ -415,6 +431,40 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         sy = (t2 % p.tiles_y) * p.TH + (r0 / p.TW) % p.TH;
         sn = (t2 / p.tiles_y) * p.TN + r0 / (p.TW * p.TH);
       }
+      // ---- column table of this tile: bias (+ FiLM of the sample each row half belongs to)
+      if (use_tab) {
+        if (local > 0) asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");   // readers of the previous tile's table
+        for (int i = et; i < 2 * BN; i += 32 * EPI_WARPS) {
+          const int hsel = i / BN, cl = i - hsel * BN;
+          const int col = n_tile * BN + cl;
+          float t = 0.f;
+          if (col < p.N) {
+            if (p.bias) t = __ldg(p.bias + col);
+            if (p.film && p.film_table) {
+              int prow;
+              if (map_row(p, m_tile, hsel * 64, prow))
+                t += __ldg(p.film + static_cast<size_t>(prow / p.rows_per_sample) * p.ldf + col);
+            }
+          }
+          coltab[i] = t;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+      }
+      // residual rows of one 32-column chunk -> registers (row per thread, 128 contiguous bytes)
+      float4 rcur[8];
+      auto load_res = [&](int c, float4 (&r)[8]) {
+        const int oc = n_tile * BN + c * 32;
+        if (my_valid && oc < n_lim) {
+          const float4* rp = reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(my_row) * p.ldr + oc);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) r[q] = rp[q];
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) r[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      if (pre_res && par < n_chunks) load_res(par, rcur);
+
       mbar_wait(&acc_full[ab], (local >> 1) & 1);
       tc_fence_after();
       if (local == 0 && threadIdx.x == 64) SDB_TR(6, clock64() - clk0);
@@ -427,24 +477,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         if (lane == 0) mbar_arrive(&acc_empty[ab]);
       }
       // ---- fused epilogue + staging + TMA store of one 32x32 chunk held in registers (row per thread)
-      auto emit = [&](float (&v)[32], int ocol0, bool fuse, bool raw_partial) {
+      auto emit = [&](float (&v)[32], int ocol0, bool fuse, bool raw_partial, const float4 (&res)[8]) {
         if (fuse) {
-          // all pointers are 16-byte aligned on this path
-          if (p.bias) {
-            const float4* bp = reinterpret_cast<const float4*>(p.bias + ocol0);
+          // alpha * acc + (bias [+ FiLM]) from the tile's column table; all pointers are 16-byte aligned on this path
+          const float4* tp = reinterpret_cast<const float4*>(coltab + (lg >= 2 ? BN : 0) + (ocol0 - n_tile * BN));
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              float4 t = __ldg(bp + q);
-              v[4 * q] = v[4 * q] * p.alpha + t.x;
-              v[4 * q + 1] = v[4 * q + 1] * p.alpha + t.y;
-              v[4 * q + 2] = v[4 * q + 2] * p.alpha + t.z;
-              v[4 * q + 3] = v[4 * q + 3] * p.alpha + t.w;
-            }
-          } else if (p.alpha != 1.0f) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+          for (int q = 0; q < 8; ++q) {
+            const float4 t = tp[q];
+            v[4 * q] = fmaf(v[4 * q], p.alpha, t.x);
+            v[4 * q + 1] = fmaf(v[4 * q + 1], p.alpha, t.y);
+            v[4 * q + 2] = fmaf(v[4 * q + 2], p.alpha, t.z);
+            v[4 * q + 3] = fmaf(v[4 * q + 3], p.alpha, t.w);
           }
-          if (p.film) {
+          if (p.film && !p.film_table) {   // rows of a tile half span several samples: FiLM per row from global
             const float4* fp = reinterpret_cast<const float4*>(p.film + static_cast<size_t>(my_sample) * p.ldf + ocol0);
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
@@ -455,15 +500,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
               v[4 * q + 3] += t.w;
             }
           }
-          if (p.residual && my_valid) {
-            const float4* rp = reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(my_row) * p.ldr + ocol0);
+          if (p.residual) {   // prefetched (zeros for rows outside the problem)
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-              float4 t = rp[q];
-              v[4 * q] += t.x;
-              v[4 * q + 1] += t.y;
-              v[4 * q + 2] += t.z;
-              v[4 * q + 3] += t.w;
+              v[4 * q] += res[q].x;
+              v[4 * q + 1] += res[q].y;
+              v[4 * q + 2] += res[q].z;
+              v[4 * q + 3] += res[q].w;
             }
           }
           if (p.act != SDB_ACT_NONE) {
@@ -550,31 +593,29 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         ++flip;
       };
 
-      const bool split_fast = p.ws && p.fast;   // raw fp32 partial planes; finished by splitk_epilogue_kernel
 #pragma unroll 1
       for (int c = par; c < n_chunks; c += 2) {
         float v[32];
+        float4 rnxt[8];
         int ocol0;
+        const bool has_next = pre_res && (c + 2 < n_chunks);
         if (geglu) {
           uint32_t xr[32], gr[32];
           tmem_ld32(taddr + c * 32, xr);
           tmem_ld32(taddr + HALF + c * 32, gr);
           tmem_ld_wait();
-          const int colx = n_tile * BN + c * 32;  // accumulator column of the value half; gate at +HALF
+          const float* tb = coltab + c * 32;   // bias of the value half; gate half at +HALF
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(xr[j]) * p.alpha;
-            float g = __uint_as_float(gr[j]) * p.alpha;
-            if (p.bias) {
-              x += __ldg(p.bias + colx + j);
-              g += __ldg(p.bias + colx + HALF + j);
-            }
+            const float x = fmaf(__uint_as_float(xr[j]), p.alpha, tb[j]);
+            const float g = fmaf(__uint_as_float(gr[j]), p.alpha, tb[HALF + j]);
             v[j] = x * gelu_erf(g);
           }
           ocol0 = n_tile * HALF + c * 32;
         } else {
           uint32_t rr[32];
           tmem_ld32(taddr + c * 32, rr);
+          if (has_next) load_res(c + 2, rnxt);   // next chunk's residual rows: in flight across this chunk's work
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
@@ -596,12 +637,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           __syncwarp();
           continue;
         }
-        emit(v, ocol0, !geglu && !split_fast, split_fast);
+        if (ocol0 < n_lim) emit(v, ocol0, !geglu && !split_fast, split_fast, rcur);   // (columns past N: nothing to write)
+        if (has_next) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) rcur[q] = rnxt[q];
+        }
       }
       // ---- per-tile flush of the fused GroupNorm column sums (see emit)
       if (p.stats && !p.ws) {
         asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");   // all smem column sums of this tile are in
-        const int et = threadIdx.x - 64;
         const int halves = p.stats_halves;
         for (int i = et; i < halves * BN; i += 32 * EPI_WARPS) {
           const int hsel = i / BN, cl = i - hsel * BN;
@@ -836,6 +880,13 @@ extern "C" int sdb_gemm(const sdb_gemm_desc* d, sdb_stream_t stream) {
   SDB_CHECK(!d->out_f16_lo || d->out_f16, "sdb_gemm: out_f16_lo needs out_f16");
 
   GemmArgs p{};
+  const int cstride = d->conv_stride > 1 ? d->conv_stride : 1;
+  SDB_CHECK(cstride == 1 || (cstride == 2 && d->taps == 9), "sdb_gemm: conv_stride must be 1 or 2 (3x3 convs only)");
+  SDB_CHECK(d->conv_shift == 0 || d->taps == 9, "sdb_gemm: conv_shift applies to 3x3 convs only");
+  const int in_h = d->in_h > 0 ? d->in_h : d->h, in_w = d->in_w > 0 ? d->in_w : d->w;
+  SDB_CHECK((in_h == d->h && in_w == d->w) || d->taps == 9, "sdb_gemm: in_h / in_w apply to 3x3 convs only");
+  p.cstride = cstride;
+  p.cshift = d->conv_shift;
   const long M = static_cast<long>(d->nb) * d->h * d->w;
   SDB_CHECK(M < (1L << 31), "sdb_gemm: M too large");
   p.M = static_cast<int>(M);
@@ -919,12 +970,17 @@ extern "C" int sdb_gemm(const sdb_gemm_desc* d, sdb_stream_t stream) {
       uint32_t box[4] = {64, 128, 1, 1};
       if (make_tmap_f16(&tm.a[i], srcs[i], 4, dims, str, box)) return 1;
     } else {
-      uint64_t dims[4] = {static_cast<uint64_t>(c), static_cast<uint64_t>(d->w), static_cast<uint64_t>(d->h),
+      // the INPUT image; a stride-2 conv traverses it with element strides {1, 2, 2, 1}: a box of 2*TW x 2*TH input
+      // positions delivers the TW x TH pixels one tap of the output tile needs
+      uint64_t dims[4] = {static_cast<uint64_t>(c), static_cast<uint64_t>(in_w), static_cast<uint64_t>(in_h),
                           static_cast<uint64_t>(d->nb)};
-      uint64_t str[3] = {static_cast<uint64_t>(c) * 2, static_cast<uint64_t>(c) * 2 * d->w,
-                         static_cast<uint64_t>(c) * 2 * d->w * d->h};
-      uint32_t box[4] = {64, static_cast<uint32_t>(p.TW), static_cast<uint32_t>(p.TH), static_cast<uint32_t>(p.TN)};
-      if (make_tmap_f16(&tm.a[i], srcs[i], 4, dims, str, box)) return 1;
+      uint64_t str[3] = {static_cast<uint64_t>(c) * 2, static_cast<uint64_t>(c) * 2 * in_w,
+                         static_cast<uint64_t>(c) * 2 * in_w * in_h};
+      uint32_t box[4] = {64, static_cast<uint32_t>(p.TW * cstride), static_cast<uint32_t>(p.TH * cstride),
+                         static_cast<uint32_t>(p.TN)};
+      uint32_t est[4] = {1, static_cast<uint32_t>(cstride), static_cast<uint32_t>(cstride), 1};
+      SDB_CHECK(box[1] <= 256 && box[2] <= 256, "sdb_gemm: strided box too large");
+      if (make_tmap(&tm.a[i], srcs[i], 2, 128, 4, dims, str, box, est)) return 1;
     }
   }
   for (int i = nsrc; i < MAX_SRC; ++i) tm.a[i] = tm.a[0];
@@ -994,6 +1050,12 @@ extern "C" int sdb_gemm(const sdb_gemm_desc* d, sdb_stream_t stream) {
       SDB_CUDA(cudaMemsetAsync(p.stats, 0, static_cast<size_t>(STAT_SLOTS) * p.n_samples * d->n * 2 * sizeof(double), st));
   }
 
+  // bias + FiLM fold into a per-tile column table when each 64-row half of every tile belongs to one sample
+  p.film_table = 0;
+  if (p.film) {
+    if (d->taps == 1) p.film_table = (p.rows_per_sample % 64 == 0) ? 1 : 0;
+    else p.film_table = (p.TW * p.TH >= 64 && p.rows_per_sample == d->h * d->w) ? 1 : 0;
+  }
   p.trace = trace_slot(8 + 8 * 160);
   int rc;
   switch (bn) {

@@ -36,7 +36,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int swizzle_bytes, int rank, const uint64_t* dims,
-              const uint64_t* strides_bytes, const uint32_t* box) {
+              const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides) {
   EncodeTiledFn fn = encode_fn();
   SDB_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
   SDB_CHECK(rank >= 1 && rank <= 5, "TMA rank %d", rank);
@@ -45,7 +45,7 @@ int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int swizzle_by
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     bx[i] = box[i];
-    es[i] = 1;
+    es[i] = elem_strides ? elem_strides[i] : 1;   // traversal stride: box[i] tensor positions yield box[i] / es[i] elements
     if (i + 1 < rank) gstr[i] = strides_bytes[i];
   }
   SDB_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base %p not 16-byte aligned", base);

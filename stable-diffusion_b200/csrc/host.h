@@ -33,7 +33,7 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
                   const uint32_t* box);
 // general form: elem_bytes 2 (fp16) or 4 (fp32); swizzle_bytes 0, 64 or 128; rank <= 5
 int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int swizzle_bytes, int rank, const uint64_t* dims,
-              const uint64_t* strides_bytes, const uint32_t* box);
+              const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides = nullptr);
 
 int sm_count();
 

@@ -8,44 +8,89 @@
 
 namespace sdb {
 
-constexpr int LS_ROWS = 8;
+constexpr int LS_ROWS = 8;      // samples per pass (activations of one pass live in shared memory)
+constexpr int LS_WARPS = 8;
+constexpr int LS_JPW = 4;       // output features per warp: their weight rows stream with 16-byte loads, all in flight
 
-__global__ void __launch_bounds__(128)
+// Weight-streaming GEMV: a warp owns LS_JPW output features; each lane reads 16-byte pieces (8 fp16) of their weight
+// rows, every load of a k-sweep issued before the first use (HBM-latency bound otherwise: the 22 emb_layers are 52 MB
+// of weights for 2 x 1280 activations). Activations are staged once per block in shared memory as fp32.
+__global__ void __launch_bounds__(32 * LS_WARPS)
     linear_small_kernel(const float* __restrict__ x, int M, int K, const __half* __restrict__ W, int N,
                         const float* __restrict__ bias, int act, float* __restrict__ out32,
                         __half* __restrict__ out16) {
+  extern __shared__ float ls_x[];   // [min(M, LS_ROWS)][K]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int j = blockIdx.x * 4 + warp;
-  if (j >= N) return;
-  const __half2* w2 = reinterpret_cast<const __half2*>(W + static_cast<size_t>(j) * K);
-  const int K2 = K >> 1;
+  const int j0 = (blockIdx.x * LS_WARPS + warp) * LS_JPW;
+  const int K8 = K >> 3;
   for (int m0 = 0; m0 < M; m0 += LS_ROWS) {
-    float acc[LS_ROWS];
+    const int mb = min(LS_ROWS, M - m0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < mb * (K >> 2); i += blockDim.x)
+      reinterpret_cast<float4*>(ls_x)[i] = reinterpret_cast<const float4*>(x + static_cast<size_t>(m0) * K)[i];
+    __syncthreads();
+    float acc[LS_JPW][LS_ROWS];
 #pragma unroll
-    for (int r = 0; r < LS_ROWS; ++r) acc[r] = 0.f;
-    for (int k2 = lane; k2 < K2; k2 += 32) {
-      float2 w = __half22float2(w2[k2]);
+    for (int jj = 0; jj < LS_JPW; ++jj)
 #pragma unroll
-      for (int r = 0; r < LS_ROWS; ++r) {
-        if (m0 + r < M) {
-          float2 xv = *reinterpret_cast<const float2*>(x + static_cast<size_t>(m0 + r) * K + 2 * k2);
-          acc[r] = fmaf(w.x, xv.x, acc[r]);
-          acc[r] = fmaf(w.y, xv.y, acc[r]);
+      for (int r = 0; r < LS_ROWS; ++r) acc[jj][r] = 0.f;
+    for (int k8 = lane; k8 < K8; k8 += 32 * 2) {
+      uint4 w[LS_JPW][2];
+#pragma unroll
+      for (int jj = 0; jj < LS_JPW; ++jj)
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int kk = k8 + u * 32;
+          w[jj][u] = (j0 + jj < N && kk < K8)
+                         ? __ldg(reinterpret_cast<const uint4*>(W + static_cast<size_t>(j0 + jj) * K) + kk)
+                         : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int kk = k8 + u * 32;
+        if (kk >= K8) break;
+#pragma unroll
+        for (int r = 0; r < LS_ROWS; ++r) {
+          if (r >= mb) break;
+          const float4 xa = *reinterpret_cast<const float4*>(ls_x + static_cast<size_t>(r) * K + kk * 8);
+          const float4 xb = *reinterpret_cast<const float4*>(ls_x + static_cast<size_t>(r) * K + kk * 8 + 4);
+#pragma unroll
+          for (int jj = 0; jj < LS_JPW; ++jj) {
+            const __half2* h = reinterpret_cast<const __half2*>(&w[jj][u]);
+            const float2 w0 = __half22float2(h[0]), w1 = __half22float2(h[1]), w2 = __half22float2(h[2]),
+                         w3 = __half22float2(h[3]);
+            float a = acc[jj][r];
+            a = fmaf(w0.x, xa.x, a);
+            a = fmaf(w0.y, xa.y, a);
+            a = fmaf(w1.x, xa.z, a);
+            a = fmaf(w1.y, xa.w, a);
+            a = fmaf(w2.x, xb.x, a);
+            a = fmaf(w2.y, xb.y, a);
+            a = fmaf(w3.x, xb.z, a);
+            a = fmaf(w3.y, xb.w, a);
+            acc[jj][r] = a;
+          }
         }
       }
     }
 #pragma unroll
-    for (int r = 0; r < LS_ROWS; ++r) {
-#pragma unroll
-      for (int o = 16; o; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
-    }
-    if (lane == 0) {
+    for (int jj = 0; jj < LS_JPW; ++jj)
 #pragma unroll
       for (int r = 0; r < LS_ROWS; ++r) {
-        if (m0 + r < M) {
-          float v = acc[r] + (bias ? bias[j] : 0.f);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) acc[jj][r] += __shfl_xor_sync(0xffffffffu, acc[jj][r], o);
+      }
+    if (lane == 0) {
+#pragma unroll
+      for (int jj = 0; jj < LS_JPW; ++jj) {
+        const int j = j0 + jj;
+        if (j >= N) break;
+#pragma unroll
+        for (int r = 0; r < LS_ROWS; ++r) {
+          if (r >= mb) break;
+          float v = acc[jj][r] + (bias ? bias[j] : 0.f);
           if (act == SDB_ACT_SILU) v = v / (1.0f + __expf(-v));
-          size_t o = static_cast<size_t>(m0 + r) * N + j;
+          const size_t o = static_cast<size_t>(m0 + r) * N + j;
           if (out32) out32[o] = v;
           if (out16) out16[o] = __float2half_rn(v);
         }
@@ -74,9 +119,19 @@ using namespace sdb;
 extern "C" int sdb_linear_small(const float* x, int32_t m, int32_t k, const void* w_f16, int32_t n, const float* bias,
                                 int32_t act, float* out_f32, void* out_f16, sdb_stream_t stream) {
   SDB_CHECK(x && w_f16 && (out_f32 || out_f16), "sdb_linear_small: null pointer");
-  SDB_CHECK(k % 2 == 0 && m > 0 && n > 0, "sdb_linear_small: bad sizes");
+  SDB_CHECK(k % 8 == 0 && m > 0 && n > 0, "sdb_linear_small: k must be a multiple of 8 (got %d)", k);
+  SDB_CHECK((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_f16) & 15) == 0,
+            "sdb_linear_small: x and w must be 16-byte aligned");
   SDB_CHECK(act == SDB_ACT_NONE || act == SDB_ACT_SILU, "sdb_linear_small: unsupported activation");
-  linear_small_kernel<<<(n + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  const size_t smem = static_cast<size_t>(m < LS_ROWS ? m : LS_ROWS) * k * sizeof(float);
+  SDB_CHECK(smem <= 200 * 1024, "sdb_linear_small: k=%d too large", k);
+  static bool configured = false;
+  if (!configured) {
+    SDB_CUDA(cudaFuncSetAttribute(linear_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+  const int per_block = LS_WARPS * LS_JPW;
+  linear_small_kernel<<<(n + per_block - 1) / per_block, 32 * LS_WARPS, smem, static_cast<cudaStream_t>(stream)>>>(
       x, m, k, static_cast<const __half*>(w_f16), n, bias, act, out_f32, static_cast<__half*>(out_f16));
   SDB_LAUNCH_CHECK();
   return 0;

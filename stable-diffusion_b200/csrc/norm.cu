@@ -123,13 +123,18 @@ __global__ void __launch_bounds__(GN_THREADS)
   }
 }
 
-// pass 2: normalise (+SiLU) -> fp16, optional raw fp16 cast. grid = (slabs, nb)
+// pass 2: normalise (+SiLU) -> fp16, optional raw fp16 cast. grid = (slabs, nb); dynamic smem: float2[C] per-channel
+// {scale, shift} so the streaming loop is one FMA (+ SiLU) per element. The element loop keeps four independent 16-byte
+// loads in flight per thread and walks (row, channel quad) incrementally (no integer division per element).
+__device__ __forceinline__ float silu_fast(float y) { return __fdividef(y, 1.0f + __expf(-y)); }
+
 __global__ void __launch_bounds__(GN_THREADS)
     gn_apply_kernel(const float* __restrict__ x0, const float* __restrict__ x1, int c0, int c1, int hw, int groups,
                     int rows_per_block, const float* __restrict__ meanrstd, const float* __restrict__ gamma,
                     const float* __restrict__ beta, float eps, int silu, __half* __restrict__ out,
                     __half* __restrict__ raw, __half* __restrict__ out_lo, __half* __restrict__ raw_lo,
                     const double* __restrict__ cs0, const double* __restrict__ cs1) {
+  extern __shared__ float2 gn_ab[];   // [C] {rstd * gamma, beta - mean * rstd * gamma}
   const int C = c0 + c1;
   const int cpg = C / groups;
   const int n = blockIdx.y;
@@ -148,8 +153,9 @@ __global__ void __launch_bounds__(GN_THREADS)
         for (int slot = 0; slot < 4; ++slot) {
           const double* q = c < c0 ? cs0 + ((static_cast<size_t>(slot) * gridDim.y + n) * c0 + c) * 2
                                    : cs1 + ((static_cast<size_t>(slot) * gridDim.y + n) * c1 + (c - c0)) * 2;
-          a += q[0];
-          b += q[1];
+          const double2 v = *reinterpret_cast<const double2*>(q);
+          a += v.x;
+          b += v.y;
         }
       }
 #pragma unroll
@@ -171,58 +177,133 @@ __global__ void __launch_bounds__(GN_THREADS)
     rstd_s[threadIdx.x] = meanrstd[(static_cast<size_t>(n) * groups + threadIdx.x) * 2 + 1];
   }
   __syncthreads();
+  for (int c = threadIdx.x; c < C; c += GN_THREADS) {
+    const int g = c / cpg;
+    const float a = rstd_s[g] * gamma[c];
+    gn_ab[c] = make_float2(a, fmaf(-mean_s[g], a, beta[c]));
+  }
+  __syncthreads();
   const int r0 = blockIdx.x * rows_per_block;
   const int r1 = min(hw, r0 + rows_per_block);
-  const int c4 = C / 4;  // C is a multiple of 4 (checked on the host); c0 too
-  const int total = (r1 - r0) * c4;
-#pragma unroll 4
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    int r = r0 + i / c4;
-    int c = (i % c4) * 4;
-    size_t row = static_cast<size_t>(n) * hw + r;
-    float4 v = c < c0 ? *reinterpret_cast<const float4*>(x0 + row * c0 + c)
-                      : *reinterpret_cast<const float4*>(x1 + row * c1 + (c - c0));
-    float in[4] = {v.x, v.y, v.z, v.w};
-    float o[4];
+  const int c4n = C >> 2;  // C is a multiple of 4 (checked on the host); c0 too
+  const int total = (r1 - r0) * c4n;
+  // position of element quad i = tid + k * GN_THREADS: (row, quad) advanced by (dr, dq) with one conditional carry
+  const int dr = GN_THREADS / c4n, dq = GN_THREADS - dr * c4n;
+  int row = r0 + threadIdx.x / c4n, quad = threadIdx.x % c4n;
+  const size_t base = static_cast<size_t>(n) * hw;
+  constexpr int U = 4;
+  for (int i = threadIdx.x; i < total; i += U * GN_THREADS) {
+    float4 v[U];
+    int rr[U], qq[U];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int g = (c + j) / cpg;
-      float y = (in[j] - mean_s[g]) * rstd_s[g] * gamma[c + j] + beta[c + j];
-      if (silu) y = y / (1.0f + __expf(-y));
-      o[j] = y;
+    for (int u = 0; u < U; ++u) {
+      rr[u] = row;
+      qq[u] = quad;
+      if (i + u * GN_THREADS < total) {
+        const int c = quad * 4;
+        const size_t r = base + row;
+        v[u] = c < c0 ? *reinterpret_cast<const float4*>(x0 + r * c0 + c)
+                      : *reinterpret_cast<const float4*>(x1 + r * c1 + (c - c0));
+      }
+      row += dr;
+      quad += dq;
+      if (quad >= c4n) {
+        quad -= c4n;
+        ++row;
+      }
     }
-    __half2 h0 = __floats2half2_rn(o[0], o[1]), h1 = __floats2half2_rn(o[2], o[3]);
-    uint2 u;
-    u.x = *reinterpret_cast<uint32_t*>(&h0);
-    u.y = *reinterpret_cast<uint32_t*>(&h1);
-    *reinterpret_cast<uint2*>(out + row * C + c) = u;
-    if (out_lo) {  // low halves of the hi/lo operand split: fp16(y - float(fp16(y)))
-      float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
-      __half2 l0 = __floats2half2_rn(o[0] - f0.x, o[1] - f0.y), l1 = __floats2half2_rn(o[2] - f1.x, o[3] - f1.y);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (i + u * GN_THREADS >= total) break;
+      const int c = qq[u] * 4;
+      const size_t o = (base + rr[u]) * C + c;
+      const float4 ab01 = *reinterpret_cast<const float4*>(&gn_ab[c]);       // {a0, b0, a1, b1}
+      const float4 ab23 = *reinterpret_cast<const float4*>(&gn_ab[c + 2]);   // {a2, b2, a3, b3}
+      const float in[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+      float y[4] = {fmaf(in[0], ab01.x, ab01.y), fmaf(in[1], ab01.z, ab01.w), fmaf(in[2], ab23.x, ab23.y),
+                    fmaf(in[3], ab23.z, ab23.w)};
+      if (silu) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) y[j] = silu_fast(y[j]);
+      }
+      __half2 h0 = __floats2half2_rn(y[0], y[1]), h1 = __floats2half2_rn(y[2], y[3]);
       uint2 w;
-      w.x = *reinterpret_cast<uint32_t*>(&l0);
-      w.y = *reinterpret_cast<uint32_t*>(&l1);
-      *reinterpret_cast<uint2*>(out_lo + row * C + c) = w;
-    }
-    if (raw) {
-      __half2 r0h = __floats2half2_rn(in[0], in[1]), r1h = __floats2half2_rn(in[2], in[3]);
-      uint2 w;
-      w.x = *reinterpret_cast<uint32_t*>(&r0h);
-      w.y = *reinterpret_cast<uint32_t*>(&r1h);
-      *reinterpret_cast<uint2*>(raw + row * C + c) = w;
-      if (raw_lo) {
-        float2 f0 = __half22float2(r0h), f1 = __half22float2(r1h);
-        __half2 l0 = __floats2half2_rn(in[0] - f0.x, in[1] - f0.y), l1 = __floats2half2_rn(in[2] - f1.x, in[3] - f1.y);
-        uint2 w2;
-        w2.x = *reinterpret_cast<uint32_t*>(&l0);
-        w2.y = *reinterpret_cast<uint32_t*>(&l1);
-        *reinterpret_cast<uint2*>(raw_lo + row * C + c) = w2;
+      w.x = *reinterpret_cast<uint32_t*>(&h0);
+      w.y = *reinterpret_cast<uint32_t*>(&h1);
+      *reinterpret_cast<uint2*>(out + o) = w;
+      if (out_lo) {  // low halves of the hi/lo operand split: fp16(y - float(fp16(y)))
+        float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+        __half2 l0 = __floats2half2_rn(y[0] - f0.x, y[1] - f0.y), l1 = __floats2half2_rn(y[2] - f1.x, y[3] - f1.y);
+        w.x = *reinterpret_cast<uint32_t*>(&l0);
+        w.y = *reinterpret_cast<uint32_t*>(&l1);
+        *reinterpret_cast<uint2*>(out_lo + o) = w;
+      }
+      if (raw) {
+        __half2 r0h = __floats2half2_rn(in[0], in[1]), r1h = __floats2half2_rn(in[2], in[3]);
+        w.x = *reinterpret_cast<uint32_t*>(&r0h);
+        w.y = *reinterpret_cast<uint32_t*>(&r1h);
+        *reinterpret_cast<uint2*>(raw + o) = w;
+        if (raw_lo) {
+          float2 f0 = __half22float2(r0h), f1 = __half22float2(r1h);
+          __half2 l0 = __floats2half2_rn(in[0] - f0.x, in[1] - f0.y), l1 = __floats2half2_rn(in[2] - f1.x, in[3] - f1.y);
+          w.x = *reinterpret_cast<uint32_t*>(&l0);
+          w.y = *reinterpret_cast<uint32_t*>(&l1);
+          *reinterpret_cast<uint2*>(raw_lo + o) = w;
+        }
       }
     }
   }
 }
 
-// LayerNorm: one warp per row, row held in registers (NPL = ceil(C / 32) elements per lane, compile-time).
+// LayerNorm: one warp per row, row held in registers. Vector variant (C a multiple of 64): NP float2 per lane,
+// coalesced 8-byte loads / 4-byte fp16x2 stores; the scalar variant covers every other width.
+template <int NP>
+__global__ void __launch_bounds__(256)
+    layernorm_v2_kernel(const float* __restrict__ x, int rows, int C, const float* __restrict__ gamma,
+                        const float* __restrict__ beta, float eps, __half* __restrict__ out, float* __restrict__ out32) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  // gamma / beta are weights: fetch them while the producer of x drains
+  float2 gm[NP], bt[NP];
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    gm[j] = __ldg(reinterpret_cast<const float2*>(gamma) + lane + j * 32);
+    bt[j] = __ldg(reinterpret_cast<const float2*>(beta) + lane + j * 32);
+  }
+  pdl_wait();
+  if (warp >= rows) return;
+  const float2* p = reinterpret_cast<const float2*>(x + static_cast<size_t>(warp) * C);
+  float2 v[NP];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    v[j] = p[lane + j * 32];
+    s += v[j].x + v[j].y;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / C;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    const float dx = v[j].x - mean, dy = v[j].y - mean;
+    q = fmaf(dx, dx, q);
+    q = fmaf(dy, dy, q);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / C + eps);
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    const float y0 = (v[j].x - mean) * rstd * gm[j].x + bt[j].x;
+    const float y1 = (v[j].y - mean) * rstd * gm[j].y + bt[j].y;
+    const size_t o = static_cast<size_t>(warp) * C + 2 * (lane + j * 32);
+    if (out) *reinterpret_cast<__half2*>(out + o) = __floats2half2_rn(y0, y1);
+    if (out32) *reinterpret_cast<float2*>(out32 + o) = make_float2(y0, y1);
+  }
+}
+
 template <int NPL>
 __global__ void __launch_bounds__(256)
     layernorm_kernel(const float* __restrict__ x, int rows, int C, const float* __restrict__ gamma,
@@ -326,12 +407,14 @@ extern "C" int sdb_groupnorm(const float* x0, const float* x1, int32_t c0, int32
                                                                       eps, partial, counter, meanrstd);
     SDB_LAUNCH_CHECK();
   }
-  // apply: enough blocks for a few waves, down to one row per block at small resolutions
-  int aslabs = std::max(1, std::min(hw, (target_blocks + nb - 1) / nb));
+  // apply: about two resident blocks per SM (each re-derives the group statistics, so fewer / fatter blocks), down to
+  // one row per block at small resolutions
+  int aslabs = std::max(1, std::min(hw, (sm_count() * 2 + nb - 1) / nb));
   int arows = (hw + aslabs - 1) / aslabs;
   aslabs = (hw + arows - 1) / arows;
   dim3 agrid(aslabs, nb);
-  SDB_CUDA(launch_pdl(gn_apply_kernel, agrid, dim3(GN_THREADS), 0, st, x0, x1, c0, c1, hw, groups, arows,
+  SDB_CUDA(launch_pdl(gn_apply_kernel, agrid, dim3(GN_THREADS), static_cast<size_t>(C) * sizeof(float2), st, x0, x1, c0, c1,
+                      hw, groups, arows,
                       static_cast<const float*>(meanrstd), gamma, beta, eps, silu, static_cast<__half*>(out_f16),
                       static_cast<__half*>(raw_f16), static_cast<__half*>(out_lo_f16),
                       static_cast<__half*>(raw_lo_f16),
@@ -351,6 +434,21 @@ extern "C" int sdb_layernorm(const float* x, int32_t rows, int32_t c, const floa
   int blocks = (rows + warps_per_block - 1) / warps_per_block;
   __half* o16 = static_cast<__half*>(out_f16);
   const int npl = (c + 31) / 32;
+  const bool al8 = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta) |
+                     reinterpret_cast<uintptr_t>(out_f32)) & 7) == 0 && (reinterpret_cast<uintptr_t>(o16) & 3) == 0;
+#define SDB_LN2(N) SDB_CUDA(launch_pdl(layernorm_v2_kernel<N>, dim3(blocks), dim3(warps_per_block * 32), 0, st, x, rows, c, gamma, beta, eps, o16, out_f32))
+  if (c % 64 == 0 && al8 && (c == 320 || c == 640 || c == 768 || c == 1280 || c == 512)) {
+    switch (c / 64) {
+      case 5: SDB_LN2(5); break;
+      case 8: SDB_LN2(8); break;
+      case 10: SDB_LN2(10); break;
+      case 12: SDB_LN2(12); break;
+      default: SDB_LN2(20); break;
+    }
+    SDB_LAUNCH_CHECK();
+    return 0;
+  }
+#undef SDB_LN2
 #define SDB_LN(N) SDB_CUDA(launch_pdl(layernorm_kernel<N>, dim3(blocks), dim3(warps_per_block * 32), 0, st, x, rows, c, gamma, beta, eps, o16, out_f32))
   if (npl <= 2) SDB_LN(2);
   else if (npl <= 4) SDB_LN(4);

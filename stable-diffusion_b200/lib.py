@@ -40,6 +40,10 @@ class GemmDesc(C.Structure):
         ("stats_out", C.c_void_p),
         ("stats_prezeroed", C.c_int32),
         ("b_dynamic", C.c_int32),
+        ("conv_stride", C.c_int32),
+        ("conv_shift", C.c_int32),
+        ("in_h", C.c_int32),
+        ("in_w", C.c_int32),
     ]
 
 

@@ -56,7 +56,7 @@ def _chk32(t, name):
 def gemm(a0, b, *, a1=None, a2=None, a3=None, nb=None, h=None, w=None, taps=1, bias=None, film=None,
          rows_per_sample=0, residual=None, act=ACT_NONE, alpha=1.0, out_f16=None, out_f32=None, out_f16_lo=None,
          want_f16=False, want_f32=False, want_lo=False, n=None, block_n=0, splits=0, workspace=None,
-         want_stats=False, b_dynamic=False):
+         want_stats=False, b_dynamic=False, conv_stride=1, conv_shift=0):
     """acc = A @ B^T with fused epilogue (see sdb_gemm in include/sdb200.h).
 
     a0 (, a1, a2, a3): fp16 [..., c_i] NHWC activations or plain [rows, c_i] matrices, concatenated along K.
@@ -76,9 +76,13 @@ def gemm(a0, b, *, a1=None, a2=None, a3=None, nb=None, h=None, w=None, taps=1, b
         srcs.append(t_)
     chans = [t_.shape[-1] for t_ in srcs]
     c0 = chans[0]
+    in_h = in_w = 0
     if taps == 9:
         assert a0.dim() == 4, "3x3 conv needs NHWC input"
         nb, h, w = a0.shape[0], a0.shape[1], a0.shape[2]
+        if conv_stride == 2:      # output size of a 3x3 / stride-2 conv: symmetric pad 1 (shift 0) or pad right/bottom (shift 1)
+            in_h, in_w = h, w
+            h, w = (in_h + 1 - conv_shift) // 2, (in_w + 1 - conv_shift) // 2
     else:
         rows = a0.numel() // c0
         nb, h, w = 1, 1, rows
@@ -111,6 +115,7 @@ def gemm(a0, b, *, a1=None, a2=None, a3=None, nb=None, h=None, w=None, taps=1, b
     d.ldo = 0
     d.block_n = block_n
     d.b_dynamic = 1 if b_dynamic else 0   # b produced by the previous kernel: no early (pre-dependency) prefetch
+    d.conv_stride, d.conv_shift, d.in_h, d.in_w = conv_stride, conv_shift, in_h, in_w
     stats = None
     if want_stats and out_f32 is not None and act != ACT_GEGLU and (taps == 9 or rows_per_sample):
         rps = rows_per_sample if rows_per_sample else h * w
@@ -131,7 +136,7 @@ def gemm(a0, b, *, a1=None, a2=None, a3=None, nb=None, h=None, w=None, taps=1, b
         d.workspace_floats = workspace.numel()
     if block_n == 0 and splits in (0, -1) and act != ACT_GEGLU:
         key = (M, n, b.shape[1], taps, len(srcs), bias is not None, film is not None, residual is not None, act,
-               out_f16 is not None, out_f32 is not None, out_f16_lo is not None, stats is not None)
+               out_f16 is not None, out_f32 is not None, out_f16_lo is not None, stats is not None, conv_stride)
         choice = TUNED.get(key)
         if choice is None and AUTOTUNE:
             choice = TUNED[key] = _tune_gemm(d, M, n, b.shape[1] // 64)

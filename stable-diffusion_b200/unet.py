@@ -238,8 +238,9 @@ class UNetModel(nn.Module):
         h = ops.linear_small(h, W["te2_w"], W["te2_b"], act=ACT_SILU)
         return ops.linear_small(h, W["emb_w"], W["emb_b"])          # [N, sum(Cout)] fp32
 
-    def _res(self, r, h, skip, film):
-        """ResBlock._forward (openaimodel.py:255-275); `skip` is the UNet skip tensor concatenated along C."""
+    def _res(self, r, h, skip, film, emit_f16=False):
+        """ResBlock._forward (openaimodel.py:255-275); `skip` is the UNet skip tensor concatenated along C.
+        emit_f16: the last GEMM also writes an fp16 copy of the block output (operand of a following stride-2 conv)."""
         nb, H, Wd, _ = h.shape
         x3 = self.W["x3"] and "ws" in r
         if x3:
@@ -257,10 +258,14 @@ class UNetModel(nn.Module):
         else:
             assert skip is None
             res = h.view(-1, r["cout"])
-        _, out = ops.gemm(hn2, r["w2"], taps=9, bias=r["b2"], residual=res, want_f32=True, splits=-1, want_stats=True)
-        return out.view(nb, H, Wd, r["cout"])
+        o16, out = ops.gemm(hn2, r["w2"], taps=9, bias=r["b2"], residual=res, want_f32=True, want_f16=emit_f16, splits=-1,
+                            want_stats=True)
+        out = out.view(nb, H, Wd, r["cout"])
+        if emit_f16:
+            out._sdb_f16 = o16.view(nb, H, Wd, r["cout"])
+        return out
 
-    def _st(self, s, x, kv):
+    def _st(self, s, x, kv, emit_f16=False):
         """SpatialTransformer.forward (attention.py:250-261) with one BasicTransformerBlock (:211-215)."""
         nb, H, Wd, ch = x.shape
         ntok = H * Wd
@@ -298,13 +303,16 @@ class UNetModel(nn.Module):
         g, _ = ops.gemm(y, s["w_ff1"], bias=s["b_ff1"], act=ACT_GEGLU, want_f16=True)
         if x3:
             t3, _, t3_lo = ops.gemm(g, s["w_ff2"], bias=s["b_ff2"], residual=t2, want_lo=True, splits=-1)
-            _, out = ops.gemm(t3, s["w_out"], a1=t3_lo, a2=t3, bias=s["b_out"], residual=x.view(-1, ch), want_f32=True,
-                              splits=-1, rows_per_sample=ntok, want_stats=True)
+            o16, out = ops.gemm(t3, s["w_out"], a1=t3_lo, a2=t3, bias=s["b_out"], residual=x.view(-1, ch), want_f32=True,
+                                want_f16=emit_f16, splits=-1, rows_per_sample=ntok, want_stats=True)
         else:
             t3, _ = ops.gemm(g, s["w_ff2"], bias=s["b_ff2"], residual=t2, want_f16=True, splits=-1)
-            _, out = ops.gemm(t3, s["w_out"], bias=s["b_out"], residual=x.view(-1, ch), want_f32=True, splits=-1,
-                              rows_per_sample=ntok, want_stats=True)
-        return out.view(nb, H, Wd, ch)
+            o16, out = ops.gemm(t3, s["w_out"], bias=s["b_out"], residual=x.view(-1, ch), want_f32=True,
+                                want_f16=emit_f16, splits=-1, rows_per_sample=ntok, want_stats=True)
+        out = out.view(nb, H, Wd, ch)
+        if emit_f16:
+            out._sdb_f16 = o16.view(nb, H, Wd, ch)
+        return out
 
     def context_kv(self, context, static=False):
         """Cross-attention K and V^T for all SpatialTransformers (x/t independent: once per prompt).
@@ -346,20 +354,25 @@ class UNetModel(nn.Module):
         return (ref._version == self._ctx_ver and context.shape == ref.shape and context.dtype == ref.dtype
                 and context.device == ref.device and bool(torch.equal(context, ref)))
 
-    def _run_layers(self, layers, h, skip, film, kvs, st_idx):
-        for kind, p in layers:
+    def _run_layers(self, layers, h, skip, film, kvs, st_idx, emit_f16=False):
+        """emit_f16: the block's output feeds a Downsample next, whose stride-2 conv reads an fp16 copy through TMA."""
+        for li, (kind, p) in enumerate(layers):
+            last = emit_f16 and li == len(layers) - 1
             if kind == "res":
-                h = self._res(p, h, skip, film)
+                h = self._res(p, h, skip, film, emit_f16=last)
                 skip = None
             elif kind == "st":
-                h = self._st(p, h, kvs[st_idx[0]])
+                h = self._st(p, h, kvs[st_idx[0]], emit_f16=last)
                 st_idx[0] += 1
             elif kind == "down":
+                # Downsample (openaimodel.py:149-153): 3x3, stride 2, pad 1, straight from the NHWC activation through
+                # strided TMA boxes (element strides {1,2,2,1}); no im2col buffer
                 nb, H, Wd, c = h.shape
-                col = ops.im2col3x3(h, 2, 1, H // 2, Wd // 2, 9 * c)
-                _, o = ops.gemm(col, p["w"], bias=p["b"], want_f32=True, splits=-1,
-                                rows_per_sample=(H // 2) * (Wd // 2), want_stats=True)
-                h = o.view(nb, H // 2, Wd // 2, c)
+                h16 = getattr(h, "_sdb_f16", None)
+                if h16 is None:
+                    h16 = ops.cast_f16(h)
+                _, o = ops.gemm(h16, p["w"], taps=9, conv_stride=2, bias=p["b"], want_f32=True, splits=-1, want_stats=True)
+                h = o.view(nb, (H + 1) // 2, (Wd + 1) // 2, c)
             elif kind == "up":
                 nb, H, Wd, c = h.shape
                 up = ops.upsample2x(h)
@@ -392,8 +405,9 @@ class UNetModel(nn.Module):
         W = self.W
         hs = []
         st_idx = [0]
-        for layers in W["input"]:
-            h = self._run_layers(layers, h, None, film, kvs, st_idx)
+        for bi, layers in enumerate(W["input"]):
+            nxt = W["input"][bi + 1] if bi + 1 < len(W["input"]) else None
+            h = self._run_layers(layers, h, None, film, kvs, st_idx, emit_f16=bool(nxt) and nxt[0][0] == "down")
             hs.append(h)
         h = self._run_layers(W["middle"], h, None, film, kvs, st_idx)
         for layers in W["output"]:

@@ -60,6 +60,31 @@ def test_conv3x3(S, cuda_dev, nb, h, w, c, n):
     assert rel_l2(o32, ref) < 1e-5, rel_l2(o32, ref)
 
 
+@pytest.mark.parametrize("nb,h,w,c,n,shift", [
+    (2, 64, 64, 320, 320, 0), (2, 32, 32, 640, 640, 0), (2, 16, 16, 1280, 1280, 0), (1, 24, 24, 64, 96, 0),
+    (1, 64, 64, 128, 128, 1), (2, 16, 16, 64, 64, 1), (1, 34, 34, 64, 32, 1),
+])
+def test_conv3x3_stride2_through_strided_tma(S, cuda_dev, nb, h, w, c, n, shift):
+    """Downsample convs without im2col: shift 0 = symmetric zero pad 1 (openaimodel.py:149-153), shift 1 = the VAE's
+    pad-right/bottom-only variant (model.py:72-76)."""
+    g = torch.Generator().manual_seed(nb * 17 + h + c + shift)
+    x = _rand16((nb, h, w, c), cuda_dev, g)
+    wt = _rand16((n, c, 3, 3), cuda_dev, g, (9 * c) ** -0.5)
+    bias = torch.randn(n, generator=g).to(cuda_dev)
+    wk = wt.permute(0, 2, 3, 1).reshape(n, 9 * c).contiguous()
+    _, o32 = S.ops.gemm(x, wk, taps=9, conv_stride=2, conv_shift=shift, bias=bias, want_f32=True, splits=-1)
+    torch.cuda.synchronize()
+    xin = x.double().permute(0, 3, 1, 2)
+    if shift:
+        ref = F.conv2d(F.pad(xin, (0, 1, 0, 1)), wt.double(), bias.double(), stride=2, padding=0)
+    else:
+        ref = F.conv2d(xin, wt.double(), bias.double(), stride=2, padding=1)
+    ho, wo = ref.shape[2], ref.shape[3]
+    assert o32.shape == (nb * ho * wo, n)
+    ref = ref.permute(0, 2, 3, 1).reshape(nb * ho * wo, n)
+    assert rel_l2(o32, ref) < 1e-5, rel_l2(o32, ref)
+
+
 def test_conv3x3_concat_and_skip(S, cuda_dev):
     g = torch.Generator().manual_seed(5)
     nb, h, w, c0, c1, n = 2, 16, 16, 128, 64, 128
