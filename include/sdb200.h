@@ -79,10 +79,12 @@ typedef struct sdb_gemm_desc {
                             bounded by workspace_floats); split-K needs workspace of splits*M*n floats */
   float* workspace;
   int64_t workspace_floats;
-  void* stats_out;       /* optional fp64 [4, M / rows_per_sample, n, 2] (4 accumulator copies, summed by the consumer): per-(sample, channel) sum and sum of squares of
-                            the fp32 output, accumulated by the epilogue (zeroed by the call) — the GroupNorm statistics
-                            of the tensor being produced, so no separate reduction pass reads it again */
-  int32_t stats_prezeroed; /* non-zero: the caller already zeroed stats_out (one arena memset per forward pass) */
+  void* stats_out;       /* optional fp32 [M / rows_per_sample, T, n / stats_group, 2]: per-tile partial {sum, sum of squares}
+                            of the fp32 output per channel group, STORED by the epilogue of the tile that owns the slot
+                            (no atomics, no zeroing, bit-reproducible) — the GroupNorm statistics of the tensor being
+                            produced, so no separate reduction pass reads it again. T comes from sdb_gemm_plan; the
+                            consumer (sdb_groupnorm) folds the T slots */
+  int32_t stats_prezeroed; /* unused (kept for layout compatibility) */
   int32_t b_dynamic;       /* non-zero: b is an activation produced by the preceding kernel (e.g. V^T = W_v . X^T swaps
                               the operand roles), so it must not be prefetched ahead of the programmatic-launch wait */
   int32_t conv_stride;     /* taps = 9 only. 0/1: stride 1. 2: stride-2 conv read straight from the NHWC input through
@@ -90,9 +92,19 @@ typedef struct sdb_gemm_desc {
   int32_t conv_shift;      /* input pixel of output o, tap t (per axis) = stride*o + t - 1 + conv_shift: 0 = zero pad 1
                               on every side (UNet), 1 = pad only right/bottom (the VAE's asymmetric F.pad, model.py:73) */
   int32_t in_h, in_w;      /* input height / width when they differ from the output's h / w (stride 2); 0 = h, w */
+  int32_t pair;            /* 0 auto, 1 single CTAs, 2 CTA pairs: two CTAs of a cluster compute one 256 x block_n tile
+                              with tcgen05.mma.cta_group::2, each loading half of the weight tile (block_n 128/160/256) */
+  int32_t splitk_mode;     /* how split-K partials meet. 0 auto, 1 fp32 planes in `workspace` + a second kernel,
+                              2 inside a thread-block cluster through distributed shared memory (2 or 4 slices, no
+                              workspace traffic, fused epilogue in the same kernel) */
+  int32_t stats_group;     /* channels per statistics entry (0/1 = per channel); must divide n and the tile width */
 } sdb_gemm_desc;
 
 int sdb_gemm(const sdb_gemm_desc* d, sdb_stream_t stream);
+/* The tile configuration sdb_gemm would use for `d` (explicit requests honoured): out[0..4] = block_n, CTAs per tile
+ * (1 | 2), split-K factor, split-K mode (0 none | 1 workspace | 2 cluster), statistics slots per sample T (0 when
+ * stats_out is NULL). stats_out, when set, is written as fp32 [samples][T][n / stats_group][2]. */
+int sdb_gemm_plan(const sdb_gemm_desc* d, int32_t* out);
 
 /*
  * Fused multi-head attention (flash-style, S/P/O in TMEM), replaces CrossAttention.forward's
@@ -130,8 +142,12 @@ int sdb_groupnorm(const float* x0, const float* x1, int32_t c0, int32_t c1, int3
                   void* out_lo_f16 /* optional low half of the normalised output (hi/lo split) */,
                   void* raw_lo_f16 /* optional low half of the raw cast */,
                   void* stats_ws /* scratch: nb * (128*groups*2 + groups*2 + 1) * 4 bytes */,
-                  const void* chan_stats0 /* optional fp64 [4, nb, c0, 2] from sdb_gemm.stats_out (skips the stats pass) */,
-                  const void* chan_stats1 /* same for x1 */, sdb_stream_t stream);
+                  const void* chan_stats0 /* optional fp32 [nb, stats_t0, c0 / stats_group, 2] from sdb_gemm.stats_out
+                                             (skips the stats pass) */,
+                  const void* chan_stats1 /* same for x1, [nb, stats_t1, c1 / stats_group, 2] */,
+                  int32_t stats_t0, int32_t stats_t1 /* partial slots per sample (sdb_gemm_plan) */,
+                  int32_t stats_group /* channels per entry; must divide c0, c1 and (c0 + c1) / groups */,
+                  sdb_stream_t stream);
 
 /* LayerNorm over the last dim of fp32 [rows, c] -> fp16 (attention.py:203-205, eps 1e-5). */
 int sdb_layernorm(const float* x, int32_t rows, int32_t c, const float* gamma, const float* beta, float eps,

@@ -101,7 +101,7 @@ except Exception as ex:  # profiler unavailable: the in-kernel trace below still
 # ---------------------------------------------------------------- 2. in-kernel phase stamps of the GEMM launches
 lib = sdb200.lib.load()
 SLOT = 8 + 8 * 160
-buf = torch.zeros(SLOT * 400, dtype=torch.int64, device=dev)
+buf = torch.zeros(SLOT * 720, dtype=torch.int64, device=dev)   # 3 passes (2 warm-up + capture) x ~210 launches
 lib.sdb_debug_trace(C.c_void_p(buf.data_ptr()), buf.numel())
 net._graphs = {}
 net.autotune = False            # TUNED already holds the choices of the first capture
@@ -123,12 +123,14 @@ h = buf.cpu().view(-1, SLOT)[2 * per_pass: 3 * per_pass]
 with open(f"gpurun_out/gemm_trace_{tag}.txt", "w") as f:
     f.write(f"traced graph replay {statistics.median(lib_ms):.3f} ms; {per_pass} gemm launches; cycles are SM clocks "
             "(median over CTAs), span/gap in us from %globaltimer\n")
-    f.write("  #      M     N  kit tap  bn sp grid | setup  wait   data  mmaend accrdy epiend |  span_us gap_us\n")
+    f.write("  #      M     N  kit tap  bn(p=pair) sp(c=cluster) grid | setup  wait   data  mmaend accrdy epiend |  span_us gap_us\n")
     prev_end = None
     tot_span = tot_gap = 0.0
     for i in range(per_pass):
         r = h[i]
         grid, bn, sp, kit, M, N, taps, tiles = [int(v) for v in r[:8]]
+        cg, bn = bn // 1000, bn % 1000
+        csk, sp = sp // 100, sp % 100
         if grid == 0:
             continue
         c = r[8: 8 + 8 * min(grid, 160)].view(-1, 8)
@@ -140,7 +142,7 @@ with open(f"gpurun_out/gemm_trace_{tag}.txt", "w") as f:
         prev_end = end
         tot_span += span
         tot_gap += gap
-        f.write(f"{i:3d} {M:6d} {N:5d} {kit:4d} {taps:3d} {bn:3d} {sp:2d} {grid:4d} | {med[0]:5d} {med[1]:5d} {med[2]:6d} "
+        f.write(f"{i:3d} {M:6d} {N:5d} {kit:4d} {taps:3d} {bn:3d}{'p' if cg == 2 else ' '}{sp:2d}{'c' if csk else ' '}{grid:4d} | {med[0]:5d} {med[1]:5d} {med[2]:6d} "
                 f"{med[3]:6d} {med[4]:6d} {med[5]:6d} | {span:8.2f} {gap:7.2f}\n")
     f.write(f"sum of gemm spans {tot_span:.0f} us, sum of gaps between gemm launches (other kernels + idle) {tot_gap:.0f} us\n")
 print(open(f"gpurun_out/gemm_trace_{tag}.txt").read()[-3000:])

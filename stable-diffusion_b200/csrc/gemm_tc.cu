@@ -1,18 +1,32 @@
-// tcgen05 GEMM / implicit-GEMM 3x3 convolution for sm_100a — persistent, warp-specialised.
+// tcgen05 GEMM / implicit-GEMM 3x3 convolution for sm_100a — persistent, warp-specialised, optionally on CTA pairs
+// (cta_group::2) and with split-K reduced inside a thread-block cluster through distributed shared memory.
 //
-//   grid        : min(#tiles, #SMs) persistent CTAs, static round-robin tile schedule (M fastest, so CTAs running
-//                 side by side read the same weight tile from L2)
+//   grid        : persistent CTAs (or CTA pairs), static round-robin tile schedule (M fastest, so CTAs running side by
+//                 side read the same weight tile from L2). Cluster split-K: one cluster per output tile instead.
 //   warp 0      : TMA producer (one elected lane) — A tile [128 rows x 64 ch] via 4-D NHWC tensor maps (3x3 taps are
-//                 shifted boxes; out-of-image reads are zero-filled by TMA = conv padding; up to four A sources are
-//                 concatenated along K: UNet skip concat, or hi/lo fp16 splits of one fp32 activation),
-//                 B tile [BN x 64] from the K-major weight matrix. STAGES-deep mbarrier ring that runs across tiles.
+//                 shifted boxes; out-of-image reads are zero-filled by TMA = conv padding; stride-2 convs traverse the
+//                 input with element strides {1,2,2,1}; up to four A sources are concatenated along K: UNet skip
+//                 concat, or hi/lo fp16 splits of one fp32 activation), B tile [BN x 64] from the K-major weight
+//                 matrix. STAGES-deep mbarrier ring that runs across tiles.
 //   warp 1      : TMEM allocation + single-thread tcgen05.mma issue (M=128, N=BN, K=16), two accumulator buffers in
 //                 TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
 //   warps 2..9  : epilogue (two warps per TMEM lane group, alternating 32-column chunks) — tcgen05.ld accumulator
 //                 rows (one row per thread), fused alpha/bias/FiLM/residual/activation in registers, 16-byte stores
 //                 into a swizzled staging tile, TMA store (cp.async.bulk.tensor) of each 32x32 block to the NHWC
-//                 output: fp16 (optionally a hi+lo pair) and/or fp32, or raw fp32 split-K partials. Outputs whose row
-//                 pitch TMA cannot address (N = 3, 4 ...) take a scalar transposed path.
+//                 output: fp16 (optionally a hi+lo pair) and/or fp32. Outputs whose row pitch TMA cannot address
+//                 (N = 3, 4 ...) take a scalar transposed path.
+//
+//   CTA pair (CG = 2): two CTAs of a cluster compute one 256 x BN tile. Each loads its own 128 rows of A and HALF of the
+//   B tile (BN/2 weight rows); the leader's single thread issues tcgen05.mma.cta_group::2 (M = 256), which reads both
+//   CTAs' shared memory and writes 128 accumulator rows into each CTA's tensor memory. Per CTA and K step the L2 -> SM
+//   traffic drops from (128 + BN) to (128 + BN/2) rows - the binding resource of these GEMMs (profiles/r02_*).
+//
+//   Cluster split-K: the S (x CG) CTAs of a cluster take K slices of one tile, exchange fp32 partials through
+//   distributed shared memory (rows scattered to their owner CTA), and each owner reduces its rows in a fixed order and
+//   runs the fused epilogue - no partial planes in HBM, no second kernel, deterministic.
+//
+//   GroupNorm statistics of the output are written as per-tile partial sums {sum, sum of squares} per channel group
+//   (plain stores into [sample][tile][N / group] - no atomics, no zeroing, bit-reproducible); the consumer folds them.
 //
 // Replaces cuDNN/cuBLAS calls behind nn.Conv2d / nn.Linear in the reference
 // (ldm/modules/diffusionmodules/openaimodel.py:204,230,241,519,685; ldm/modules/attention.py:40-60,161-168,233-248).
@@ -21,6 +35,7 @@
 #include "ptx.cuh"
 
 #include <algorithm>
+#include <stdlib.h>
 
 namespace sdb {
 
@@ -31,12 +46,12 @@ constexpr int MAX_SRC = 4;
 constexpr int EPI_WARPS = 8;
 constexpr int STG_WARP_BYTES = 8192;  // per epilogue warp: 2 x 4 KB fp32 tiles, or 2 x (2 KB hi + 2 KB lo) fp16 tiles
 constexpr int STAGING_BYTES = EPI_WARPS * STG_WARP_BYTES;
-constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
-constexpr int STAT_SLOTS = 4;   // fused GroupNorm statistics are spread over 4 accumulator copies (m_tile & 3)
+constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS + 32;   // + warp 10: weight (B) tile producer
+constexpr int B_WARP = 2 + EPI_WARPS;
 
 struct TmapPack {
   CUtensorMap a[MAX_SRC];
-  CUtensorMap b;
+  CUtensorMap b;     // box {64, BN / CG}
   CUtensorMap o32;   // fp32 output (or the split-K workspace), 5-D [C, W, H, NB, S], box {32, bw, bh, bn, 1}, SWIZZLE_128B
   CUtensorMap o16;   // fp16 output, same geometry, SWIZZLE_64B
   CUtensorMap o16lo; // fp16 low half
@@ -51,6 +66,8 @@ struct GemmArgs {
   int TW, TH, TN, tiles_x, tiles_y;
   int k_iters, iters_per_split, splits;
   int m_tiles, n_tiles;
+  int m_units;          // m_tiles for single CTAs, ceil(m_tiles / 2) for CTA pairs
+  int csk;              // cluster split-K: the `splits` (x CG) CTAs of a cluster share one output tile
   float alpha;
   const float* bias;
   const float* film;
@@ -64,8 +81,11 @@ struct GemmArgs {
   int ldo;
   float* ws;
   int act;
-  double* stats;    // optional per-(sample, channel) {sum, sum of squares} of the fp32 output (GroupNorm statistics)
-  int stats_halves;       // 1: the 128 rows of a tile belong to one sample; 2: rows 0-63 / 64-127 to two samples
+  float2* stats;    // optional per-tile GroupNorm partials [n_samples][stats_T][N / stats_sg] {sum, sum of squares}
+  int stats_halves; // 1: the 128 rows of a tile belong to one sample; 2: rows 0-63 / 64-127 to two samples
+  int stats_T;      // partial slots per sample
+  int stats_sg;     // channels per statistics entry
+  int stats_tps;    // 3x3 geometry: tiles per sample (tiles_x * tiles_y)
   int n_samples;
   int b_static;     // B is a weight matrix: safe to prefetch before griddepcontrol.wait
   int fast;         // outputs go through the TMA-store epilogue
@@ -74,6 +94,8 @@ struct GemmArgs {
   int film_table;   // 1: rows 0-63 / 64-127 of every tile belong to one sample each, so bias + FiLM fold into a
                     // per-tile shared-memory column table; 0: FiLM is read per row from global memory
   unsigned long long* trace;  // debug: per-CTA phase timestamps (sdb_debug_trace), NULL in production
+  int dbg;                    // debug (env SDB_DBG): bit 0 no statistics loop, 1 no statistics flush, 2 no TMA stores,
+                              // 3 no B loads, 4 no MMAs, 5 no A loads (timing experiments; results are garbage)
 };
 
 // Exact-erf GELU (attention.py:44, F.gelu default) with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far
@@ -206,55 +228,90 @@ __device__ __forceinline__ unsigned long long gtimer() {
 // debug trace: word w of this CTA's record (8 words per CTA after an 8-word launch header)
 #define SDB_TR(w, val)                                                          \
   do {                                                                          \
-    if (p.trace) p.trace[8 + blockIdx.x * 8 + (w)] = (val);                     \
+    if (p.trace && blockIdx.x < 160) p.trace[8 + blockIdx.x * 8 + (w)] = (val); \
   } while (0)
 
-template <int BN>
+// DEEP: every CTA computes exactly ONE tile (grid <= resident CTAs, or cluster split-K). The epilogue then starts only
+// after the last MMA has retired, so its staging tiles alias the tail of the operand ring and the whole shared memory
+// (~210 KB) is pipeline: the main loop of these GEMMs is bound by the load round trip (TMA issue -> L2 -> MMA -> commit
+// -> slot free, ~2300 clk), i.e. by the bytes in flight per SM (profiles/r02_epilogue_probe.txt). Persistent multi-tile
+// CTAs keep a separate staging area (the epilogue of tile i overlaps the main loop of tile i+1) and fewer stages.
+template <int BN, int CG, bool DEEP>
 struct GemmCfg {
-  static constexpr int STAGES = BN <= 32 ? 6 : BN <= 64 ? 6 : BN <= 128 ? 4 : BN <= 160 ? 4 : 3;
+  static constexpr int B_ROWS = BN / CG;            // weight rows of the tile this CTA loads
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = DEEP ? (CG == 2 ? (BN <= 128 ? 9 : BN <= 160 ? 8 : 6)
+                                                : (BN <= 32 ? 10 : BN <= 64 ? 9 : BN <= 160 ? 6 : 4))
+                                     : (CG == 2 ? (BN <= 128 ? 6 : BN <= 160 ? 5 : 4) : (BN <= 64 ? 6 : BN <= 160 ? 4 : 3));
   static constexpr int TMEM_COLS = BN <= 32 ? 64 : BN <= 64 ? 128 : BN <= 128 ? 256 : 512;  // two accumulators
-  static constexpr int SMEM = STAGES * (A_BYTES + BN * BK * 2) + STAGING_BYTES + 1024;
+  static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
+  static constexpr int SMEM = RING_BYTES + (DEEP ? 0 : STAGING_BYTES) + 1024;
+  static_assert(!DEEP || RING_BYTES >= BN * 512 + STAGING_BYTES, "cluster split-K receive area + staging must fit the ring");
 };
 
-template <int BN>
+struct EpiRows {   // the output rows one epilogue warp handles: row per lane + the TMA store box origin
+  int row, sample;
+  bool valid;
+  int sx, sy, sn;
+};
+
+template <int BN, int CG, bool DEEP>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TmapPack tm, const GemmArgs p) {
-  constexpr int STAGES = GemmCfg<BN>::STAGES;
-  constexpr int B_BYTES = BN * BK * 2;
-  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr int TMEM_COLS = GemmCfg<BN>::TMEM_COLS;
+  using Cfg = GemmCfg<BN, CG, DEEP>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int B_ROWS = Cfg::B_ROWS;
+  constexpr int STAGE_BYTES = Cfg::STAGE_BYTES;
+  constexpr int TMEM_COLS = Cfg::TMEM_COLS;
 
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment by offset (keeps the shared address space visible to the compiler: LDS/STS, not generic)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* staging = smem + STAGES * STAGE_BYTES;
+  uint8_t* staging = smem + Cfg::RING_BYTES - (DEEP ? STAGING_BYTES : 0);   // DEEP: aliases the last stages (idle by then)
   __shared__ uint64_t full_bar[STAGES];
   __shared__ uint64_t empty_bar[STAGES];
   __shared__ uint64_t acc_full[2];
   __shared__ uint64_t acc_empty[2];
   __shared__ uint32_t tmem_base_smem;
-  // fused GroupNorm statistics: [lane group][column][sum, sum of squares]; one writer per slot per tile and a
-  // fixed-order fold at the flush (deterministic; the cross-CTA combine uses fp64 atomics)
-  __shared__ float colsum[4 * BN * 2];
+  // fused GroupNorm statistics: [lane group][column][sum, sum of squares]; one writer per slot per tile, fixed-order
+  // fold at the flush, plain stores of the per-tile partials (deterministic)
+  __shared__ __align__(16) float colsum[4 * BN * 2];
   // per-tile column constants of the fused epilogue: bias[col] (+ FiLM[sample of the row half][col]), so the chunk
   // loop reads them from shared memory instead of paying a global-load latency per chunk
   __shared__ __align__(16) float coltab[2 * BN];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int tiles_total = p.m_tiles * p.n_tiles * p.splits;
   pdl_launch_dependents();   // the next kernel may start its prologue while this one runs
   const long long clk0 = clock64();
+
+  // ---- cluster coordinates. CTA pair: ranks (2k, 2k+1), the even one leads. Cluster split-K: rank / CG = K slice.
+  const bool clustered = (CG == 2) || (p.csk != 0);
+  const uint32_t crank = clustered ? cluster_ctarank() : 0u;
+  const uint32_t pr = CG == 2 ? (crank & 1u) : 0u;
+  const uint32_t lead = crank - pr;
+  const int csplit = p.csk ? static_cast<int>(crank) / CG : 0;
+  const int n_units = p.m_units * p.n_tiles * (p.csk ? 1 : p.splits);
+  const int unit0 = p.csk ? static_cast<int>(blockIdx.x) / (p.splits * CG) : static_cast<int>(blockIdx.x) / CG;
+  const int ustride = p.csk ? (1 << 30) : static_cast<int>(gridDim.x) / CG;
+  auto decode = [&](int u, int& m_tile, int& n_tile, int& split) {
+    const int mu = u % p.m_units;
+    const int rest = u / p.m_units;
+    n_tile = rest % p.n_tiles;
+    split = p.csk ? csplit : rest / p.n_tiles;
+    m_tile = mu * CG + static_cast<int>(pr);
+  };
   if (p.trace && threadIdx.x == 0) {
     SDB_TR(0, gtimer());
     if (blockIdx.x == 0) {
       p.trace[0] = gridDim.x;
-      p.trace[1] = BN;
-      p.trace[2] = p.splits;
+      p.trace[1] = BN + 1000 * CG;
+      p.trace[2] = p.splits + 100 * p.csk;
       p.trace[3] = p.k_iters;
       p.trace[4] = p.M;
       p.trace[5] = p.N;
       p.trace[6] = p.taps;
-      p.trace[7] = tiles_total;
+      p.trace[7] = n_units;
     }
   }
 
@@ -268,202 +325,455 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       if (p.out_f16_lo) tma_prefetch_desc(&tm.o16lo);
     }
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], 1);      // CTA pair: armed by the leader alone, with the bytes of BOTH CTAs
       mbar_init(&empty_bar[s], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], EPI_WARPS);
+      mbar_init(&acc_empty[i], EPI_WARPS * CG);
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(&tmem_base_smem, TMEM_COLS);
-    tmem_relinquish();
+    if (CG == 2) {
+      tmem_alloc_cg2(&tmem_base_smem, TMEM_COLS);
+      tmem_relinquish_cg2();
+    } else {
+      tmem_alloc(&tmem_base_smem, TMEM_COLS);
+      tmem_relinquish();
+    }
+  }
+  if (p.csk && p.stats) {   // lane groups this CTA does not own contribute zeros to its statistics
+    for (int i = threadIdx.x; i < 4 * BN * 2; i += GEMM_THREADS) colsum[i] = 0.f;
   }
   tc_fence_before();
-  __syncthreads();
+  if (clustered) cluster_sync_all();   // barrier inits visible to the peer before any remote arrive
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = tmem_base_smem;
   if (threadIdx.x == 0) SDB_TR(2, clock64() - clk0);
 
-  if (warp == 0) {
-    if (elect_one()) {
-      uint32_t i = 0;  // ring position, continues across tiles
-      // PDL: the weight (B) tiles do not depend on the previous kernel — start streaming them for the first ring
-      // pass of the first tile before waiting for the producer of the activations
-      int npre = 0;
-      if (p.b_static && blockIdx.x < tiles_total) {
-        const int rest0 = blockIdx.x / p.m_tiles;
-        const int n_tile0 = rest0 % p.n_tiles;
-        const int split0 = rest0 / p.n_tiles;
-        const int b0 = split0 * p.iters_per_split;
-        const int e0 = min(p.k_iters, b0 + p.iters_per_split);
-        npre = min(STAGES, e0 - b0);
-        for (int j = 0; j < npre; ++j) {
-          mbar_arrive_expect_tx(&full_bar[j], STAGE_BYTES);
-          tma_load_2d(smem + j * STAGE_BYTES + A_BYTES, &tm.b, &full_bar[j], (b0 + j) * BK, n_tile0 * BN);
+  // ---------------------------------------------------------------- epilogue state and helpers (warps 2..9)
+  const int ew = (warp - 2) & 7;
+  const int lg = warp & 3;       // TMEM lane group of this warp
+  const int par = ew >> 2;       // the two warps of a lane group alternate chunks
+  const int et = threadIdx.x - 64;
+  uint8_t* stg = staging + ew * STG_WARP_BYTES;
+  const bool geglu = (p.act == SDB_ACT_GEGLU) && !p.ws;
+  constexpr int HALF = BN / 2;
+  const int n_chunks = geglu ? HALF / 32 : BN / 32;
+  const int n_lim = geglu ? p.N / 2 : p.N;   // output columns that exist
+  const bool st32 = p.ws || p.out_f32;       // an fp32 tile is staged in some phase (output or split-K partial)
+  const bool st16 = p.out_f16 != nullptr;
+  // staging buffers per chunk parity: fp32 tiles 4 KB each; fp16 hi 2 KB + lo 2 KB each (fp32+fp16 together: single)
+  const bool dbl = !(st32 && st16);
+  const bool split_fast = p.ws && p.fast;    // raw fp32 partial planes; finished by splitk_epilogue_kernel
+  const bool use_tab = p.fast && !split_fast;
+  const bool pre_res = use_tab && !geglu && p.residual != nullptr;
+  uint32_t flip = 0;
+
+  auto rows_of = [&](int m_tile, int lgx) {
+    EpiRows rw;
+    rw.valid = map_row(p, m_tile, lgx * 32 + lane, rw.row);
+    rw.sample = rw.valid ? rw.row / p.rows_per_sample : 0;
+    if (p.taps == 1) {
+      rw.sx = m_tile * BM + lgx * 32;
+      rw.sy = 0;
+      rw.sn = 0;
+    } else {
+      const int tx = m_tile % p.tiles_x;
+      const int t2 = m_tile / p.tiles_x;
+      const int r0 = lgx * 32;
+      rw.sx = tx * p.TW + r0 % p.TW;
+      rw.sy = (t2 % p.tiles_y) * p.TH + (r0 / p.TW) % p.TH;
+      rw.sn = (t2 / p.tiles_y) * p.TN + r0 / (p.TW * p.TH);
+    }
+    return rw;
+  };
+  // column table of a tile: bias (+ FiLM of the sample each row half belongs to); all epilogue warps take part
+  auto fill_coltab = [&](int m_tile, int n_tile, bool first) {
+    if (!first) asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");   // readers of the previous tile's table
+    for (int i = et; i < 2 * BN; i += 32 * EPI_WARPS) {
+      const int hsel = i / BN, cl = i - hsel * BN;
+      const int col = n_tile * BN + cl;
+      float t = 0.f;
+      if (col < p.N) {
+        if (p.bias) t = __ldg(p.bias + col);
+        if (p.film && p.film_table) {
+          int prow;
+          if (map_row(p, m_tile, hsel * 64, prow))
+            t += __ldg(p.film + static_cast<size_t>(prow / p.rows_per_sample) * p.ldf + col);
         }
       }
-      pdl_wait();
-      SDB_TR(3, clock64() - clk0);
-      for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
-        const int m_tile = tile % p.m_tiles;
-        const int rest = tile / p.m_tiles;
-        const int n_tile = rest % p.n_tiles;
-        const int split = rest / p.n_tiles;
+      coltab[i] = t;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+  };
+  // residual rows of one 32-column chunk -> registers (row per thread, 128 contiguous bytes)
+  auto load_res = [&](const EpiRows& rw, int n_tile, int c, float4 (&r)[8]) {
+    const int oc = n_tile * BN + c * 32;
+    if (rw.valid && oc < n_lim) {
+      const float4* rp = reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(rw.row) * p.ldr + oc);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) r[q] = rp[q];
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) r[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  // fused epilogue + staging + TMA store of one 32x32 chunk held in registers (row per thread); lgx = lane group of
+  // the rows (selects the sample half of the column table and the statistics slot)
+  auto emit = [&](float (&v)[32], int ocol0, int n_tile, int split, const EpiRows& rw, int lgx, bool fuse,
+                  bool raw_partial, const float4 (&res)[8]) {
+    if (fuse) {
+      // alpha * acc + (bias [+ FiLM]) from the tile's column table; all pointers are 16-byte aligned on this path
+      const float4* tp = reinterpret_cast<const float4*>(coltab + (lgx >= 2 ? BN : 0) + (ocol0 - n_tile * BN));
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 t = tp[q];
+        v[4 * q] = fmaf(v[4 * q], p.alpha, t.x);
+        v[4 * q + 1] = fmaf(v[4 * q + 1], p.alpha, t.y);
+        v[4 * q + 2] = fmaf(v[4 * q + 2], p.alpha, t.z);
+        v[4 * q + 3] = fmaf(v[4 * q + 3], p.alpha, t.w);
+      }
+      if (p.film && !p.film_table) {   // rows of a tile half span several samples: FiLM per row from global
+        const float4* fp = reinterpret_cast<const float4*>(p.film + static_cast<size_t>(rw.sample) * p.ldf + ocol0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 t = __ldg(fp + q);
+          v[4 * q] += t.x;
+          v[4 * q + 1] += t.y;
+          v[4 * q + 2] += t.z;
+          v[4 * q + 3] += t.w;
+        }
+      }
+      if (p.residual) {   // prefetched (zeros for rows outside the problem)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          v[4 * q] += res[q].x;
+          v[4 * q + 1] += res[q].y;
+          v[4 * q + 2] += res[q].z;
+          v[4 * q + 3] += res[q].w;
+        }
+      }
+      if (p.act != SDB_ACT_NONE) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+      }
+    }
+    const bool w32 = raw_partial || p.out_f32;
+    const bool w16 = !raw_partial && p.out_f16;
+    const bool w16lo = w16 && p.out_f16_lo;
+    // staging buffer for this chunk; make sure the TMA store that last read it has finished reading
+    const uint32_t bsel = dbl ? (flip & 1) : 0;
+    if (lane == 0) {
+      if (dbl) tma_store_wait_read<1>();
+      else tma_store_wait_read<0>();
+    }
+    __syncwarp();
+    uint8_t* s32 = stg + bsel * 4096;
+    uint8_t* s16 = st32 ? stg + 4096 : stg + bsel * 4096;
+    uint8_t* s16l = s16 + 2048;
+    if (w32) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<float4*>(s32 + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+            make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+    if (w16) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        __half2 h[4];
+        uint4 u, ul;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[8 * q + 2 * e], v[8 * q + 2 * e + 1]);
+        u.x = *reinterpret_cast<uint32_t*>(&h[0]);
+        u.y = *reinterpret_cast<uint32_t*>(&h[1]);
+        u.z = *reinterpret_cast<uint32_t*>(&h[2]);
+        u.w = *reinterpret_cast<uint32_t*>(&h[3]);
+        const uint32_t off = lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4);
+        *reinterpret_cast<uint4*>(s16 + off) = u;
+        if (w16lo) {
+          __half2 l[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float2 hf = __half22float2(h[e]);
+            l[e] = __floats2half2_rn(v[8 * q + 2 * e] - hf.x, v[8 * q + 2 * e + 1] - hf.y);
+          }
+          ul.x = *reinterpret_cast<uint32_t*>(&l[0]);
+          ul.y = *reinterpret_cast<uint32_t*>(&l[1]);
+          ul.z = *reinterpret_cast<uint32_t*>(&l[2]);
+          ul.w = *reinterpret_cast<uint32_t*>(&l[3]);
+          *reinterpret_cast<uint4*>(s16l + off) = ul;
+        }
+      }
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0 && !(p.dbg & 4)) {
+      if (raw_partial) {
+        tma_store_5d(&tm.ows, s32, ocol0, rw.sx, rw.sy, rw.sn, split);
+      } else {
+        if (w32) tma_store_5d(&tm.o32, s32, ocol0, rw.sx, rw.sy, rw.sn, 0);
+        if (w16) tma_store_5d(&tm.o16, s16, ocol0, rw.sx, rw.sy, rw.sn, 0);
+        if (w16lo) tma_store_5d(&tm.o16lo, s16l, ocol0, rw.sx, rw.sy, rw.sn, 0);
+      }
+      tma_store_commit();
+    }
+    if (!raw_partial && p.stats && w32 && !(p.dbg & 1)) {
+      // GroupNorm statistics of the value just produced, from the staged 32x32 fp32 tile: lane l reads the 16-byte
+      // granule (l & 7) of rows (l >> 3) + 4k (8 independent LDS.128, conflict-free), two butterfly steps fold the four
+      // row classes, lanes 0-7 then hold the sums of columns 4*(l & 7) .. +3 and write the CTA's shared column sums
+      // (flushed once per tile)
+      const uint32_t vmask = __ballot_sync(0xffffffffu, rw.valid);
+      const int gq = lane & 7, rb = lane >> 3;
+      float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int r = rb + 4 * k;
+        float4 x = *reinterpret_cast<const float4*>(s32 + r * 128 + ((gq ^ (r & 7)) << 4));
+        const float keep = ((vmask >> r) & 1u) ? 1.0f : 0.0f;   // rows outside the problem hold bias-only garbage
+        x.x *= keep;
+        x.y *= keep;
+        x.z *= keep;
+        x.w *= keep;
+        cs[0] += x.x;
+        cs[1] += x.y;
+        cs[2] += x.z;
+        cs[3] += x.w;
+        cq[0] = fmaf(x.x, x.x, cq[0]);
+        cq[1] = fmaf(x.y, x.y, cq[1]);
+        cq[2] = fmaf(x.z, x.z, cq[2]);
+        cq[3] = fmaf(x.w, x.w, cq[3]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 8);
+        cq[j] += __shfl_xor_sync(0xffffffffu, cq[j], 8);
+        cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 16);
+        cq[j] += __shfl_xor_sync(0xffffffffu, cq[j], 16);
+      }
+      if (lane < 8) {
+        const int cl = ocol0 - n_tile * BN + 4 * gq;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<float2*>(&colsum[(lgx * BN + cl + j) * 2]) = make_float2(cs[j], cq[j]);
+      }
+    }
+    ++flip;
+  };
+  // per-tile flush of the fused GroupNorm column sums: one {sum, sum of squares} entry per group of stats_sg
+  // channels, stored (not accumulated) into the slot only this tile owns
+  auto flush_stats = [&](int m_tile, int n_tile) {
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");   // all smem column sums of this tile are in
+    const int sg = p.stats_sg;
+    const int gpt = BN / sg;       // BN % sg == 0 (checked on the host)
+    const int E = p.N / sg;
+    const int halves = p.stats_halves;
+    for (int i = et; i < halves * gpt; i += 32 * EPI_WARPS) {
+      const int hsel = i / gpt, g = i - hsel * gpt;
+      const int col0 = n_tile * BN + g * sg;
+      int prow;
+      const bool pv = map_row(p, m_tile, hsel * 64, prow);   // first tile row of this half
+      if (pv && col0 < p.N) {
+        const int s = prow / p.rows_per_sample;
+        int t;
+        if (p.taps == 1) t = halves == 1 ? (prow % p.rows_per_sample) / BM : 0;
+        else t = m_tile % p.stats_tps;   // spatial tile position (each half of a two-sample tile has its own sample)
+        if (p.csk) t = t * p.splits + csplit;
+        float a = 0.f, b = 0.f;
+        for (int j = 0; j < sg; ++j) {
+          const int cl = g * sg + j;
+          if (halves == 2) {
+            a += colsum[((2 * hsel) * BN + cl) * 2] + colsum[((2 * hsel + 1) * BN + cl) * 2];
+            b += colsum[((2 * hsel) * BN + cl) * 2 + 1] + colsum[((2 * hsel + 1) * BN + cl) * 2 + 1];
+          } else {
+            a += (colsum[cl * 2] + colsum[(BN + cl) * 2]) + (colsum[(2 * BN + cl) * 2] + colsum[(3 * BN + cl) * 2]);
+            b += (colsum[cl * 2 + 1] + colsum[(BN + cl) * 2 + 1]) +
+                 (colsum[(2 * BN + cl) * 2 + 1] + colsum[(3 * BN + cl) * 2 + 1]);
+          }
+        }
+        p.stats[(static_cast<size_t>(s) * p.stats_T + t) * E + col0 / sg] = make_float2(a, b);
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");   // slots consumed before the next tile rewrites them
+  };
+
+  // ---------------------------------------------------------------- roles
+  if (warp == 0 || warp == B_WARP) {
+    // Two single-thread producers: warp 0 streams the activation (A) tiles and arms the stage barriers, warp 10 streams
+    // the weight (B) tiles. One thread issuing both was the bottleneck of the whole main loop (~590 clk per K step of
+    // wait + index arithmetic + two TMA issues against a 320 clk MMA budget, profiles/r02_mainloop_probe.txt); all loop
+    // state is advanced incrementally (no division in the loop). Static weights do not depend on the previous kernel:
+    // their producer never executes griddepcontrol.wait and runs ahead under programmatic dependent launch.
+    if (elect_one()) {
+      // CTA pair: the loads of both CTAs complete on the LEADER's full barrier (its MMA thread consumes both halves).
+      // Only the leader arms it - locally, with the bytes of both CTAs; completions of the peer's loads that overtake the
+      // arming just drive the transaction count negative for a moment (a remote arrive per stage would put a cluster
+      // round trip into the producer's issue loop).
+      const bool is_a = warp == 0;
+      const uint32_t full_base = CG == 2 ? mapa_shared(smem_u32(&full_bar[0]), lead) : smem_u32(&full_bar[0]);
+      const uint32_t arm_bytes = (((p.dbg & 8) ? 0u : Cfg::B_BYTES) + ((p.dbg & 32) ? 0u : A_BYTES)) * CG;
+      const uint32_t smem_base = smem_u32(smem) + (is_a ? 0u : static_cast<uint32_t>(A_BYTES));
+      if (is_a || !p.b_static) pdl_wait();
+      if (is_a) SDB_TR(3, clock64() - clk0);
+      int s = 0;
+      uint32_t ph = 0;
+      bool ring_pass = false;
+      uint32_t dst = smem_base, bar = full_base;
+      const int cpt = p.cb[p.nsrc];
+      for (int u = unit0; u < n_units; u += ustride) {
+        int m_tile, n_tile, split;
+        decode(u, m_tile, n_tile, split);
         const int it_begin = split * p.iters_per_split;
         const int it_end = min(p.k_iters, it_begin + p.iters_per_split);
+        // A: position inside the (tap, source, 64-channel chunk) sequence, advanced per K step
         int x0 = 0, y0 = 0, n0 = 0;
         if (p.taps == 1) {
           x0 = m_tile * BM;
         } else {
           int tx = m_tile % p.tiles_x;
           int t2 = m_tile / p.tiles_x;
-          x0 = tx * p.TW;
-          y0 = (t2 % p.tiles_y) * p.TH;
+          x0 = tx * p.TW * p.cstride + p.cshift;
+          y0 = (t2 % p.tiles_y) * p.TH * p.cstride + p.cshift;
           n0 = (t2 / p.tiles_y) * p.TN;
         }
-        const int cpt = p.cb[p.nsrc];
-        for (int it = it_begin; it < it_end; ++it, ++i) {
-          const int s = i % STAGES;
-          const uint32_t ph = (i / STAGES) & 1;
-          const bool prefetched = static_cast<int>(i) < npre;   // B already in flight, barrier already armed
-          if (!prefetched) {
-            mbar_wait(&empty_bar[s], ph ^ 1);
-            mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+        int tap = it_begin / cpt, cc = it_begin - tap * cpt;
+        int dx = 0, dy = 0;
+        if (p.taps == 9) {
+          dy = tap / 3 - 1;
+          dx = tap - (tap / 3) * 3 - 1;
+        }
+        int src = 0;
+        while (src + 1 < p.nsrc && cc >= p.cb[src + 1]) ++src;
+        int cend = p.cb[src + 1];
+        int c0 = (cc - p.cb[src]) * BK;
+        const CUtensorMap* amap = &tm.a[src];
+        int kb = it_begin * BK;
+        const int nrow = n_tile * BN + static_cast<int>(pr) * B_ROWS;
+        for (int it = it_begin; it < it_end; ++it) {
+          if (ring_pass) mbar_wait(&empty_bar[s], ph ^ 1);   // (first pass over the ring: every slot is free)
+          if (is_a) {
+            if (pr == 0) mbar_arrive_expect_tx(&full_bar[s], arm_bytes);
+            if (!(p.dbg & 32)) {
+              if (CG == 2) tma_load_4d_cg2_addr(dst, amap, bar, c0, x0 + dx, y0 + dy, n0);
+              else tma_load_4d_addr(dst, amap, bar, c0, x0 + dx, y0 + dy, n0);
+            }
+            // next K step: chunk -> source -> tap
+            c0 += BK;
+            if (++cc == cend) {
+              if (cc == cpt) {
+                cc = 0;
+                src = 0;
+                if (++dx == 2) {
+                  dx = -1;
+                  ++dy;
+                }
+              } else {
+                ++src;
+              }
+              c0 = 0;
+              cend = p.cb[src + 1];
+              amap = &tm.a[src];
+            }
+          } else {
+            if (!(p.dbg & 8)) {
+              if (CG == 2) tma_load_2d_cg2_addr(dst, &tm.b, bar, kb, nrow);
+              else tma_load_2d_addr(dst, &tm.b, bar, kb, nrow);
+            }
+            kb += BK;
           }
-          const int tap = it / cpt;
-          const int cc = it - tap * cpt;
-          int dx = 0, dy = 0;
-          if (p.taps == 9) {
-            dy = tap / 3 - 1;
-            dx = tap % 3 - 1;
+          dst += STAGE_BYTES;
+          bar += 8;
+          if (++s == STAGES) {
+            s = 0;
+            ph ^= 1;
+            dst = smem_base;
+            bar = full_base;
+            ring_pass = true;
           }
-          int src = 0;
-          while (src + 1 < p.nsrc && cc >= p.cb[src + 1]) ++src;
-          uint8_t* a_s = smem + s * STAGE_BYTES;
-          tma_load_4d(a_s, &tm.a[src], &full_bar[s], (cc - p.cb[src]) * BK, x0 * p.cstride + dx + p.cshift,
-                      y0 * p.cstride + dy + p.cshift, n0);
-          if (!prefetched) tma_load_2d(a_s + A_BYTES, &tm.b, &full_bar[s], it * BK, n_tile * BN);
         }
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
-    if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
-      uint32_t i = 0, local = 0;
-      for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x, ++local) {
-        const int split = (tile / p.m_tiles) / p.n_tiles;
+    if (pr == 0 && elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_f16(BM * CG, BN);
+      const uint16_t cmask = static_cast<uint16_t>(3u << lead);   // the two CTAs of this pair
+      // descriptor low words advance with the stage (start address >> 4); the high word is constant
+      const uint32_t desc_lo0 = (smem_u32(smem) & 0x3FFFFu) >> 4;
+      constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
+      uint32_t local = 0;
+      int s = 0;
+      uint32_t ph = 0, dlo = desc_lo0;
+      bool first_data = true;
+      for (int u = unit0; u < n_units; u += ustride, ++local) {
+        int m_tile, n_tile, split;
+        decode(u, m_tile, n_tile, split);
         const int it_begin = split * p.iters_per_split;
         const int it_end = min(p.k_iters, it_begin + p.iters_per_split);
         const uint32_t ab = local & 1;
-        mbar_wait(&acc_empty[ab], ((local >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+        mbar_wait(&acc_empty[ab], ((local >> 1) & 1) ^ 1);  // epilogue(s) have drained this accumulator
         tc_fence_after();
         const uint32_t d_addr = tmem_d + ab * BN;
-        for (int it = it_begin; it < it_end; ++it, ++i) {
-          const int s = i % STAGES;
-          const uint32_t ph = (i / STAGES) & 1;
+        uint32_t acc = 0;
+        for (int it = it_begin; it < it_end; ++it) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          if (i == 0) SDB_TR(4, clock64() - clk0);
-          const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
-          const uint64_t da = umma_desc_k128(a_addr);
-          const uint64_t db = umma_desc_k128(a_addr + A_BYTES);
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advance 32 bytes (16 fp16) along K inside the 128-byte swizzle atom: +2 in the (addr>>4) field
-            umma_f16(d_addr, da + 2 * k, db + 2 * k, idesc, (it > it_begin || k > 0) ? 1u : 0u);
+          if (first_data) {
+            SDB_TR(4, clock64() - clk0);
+            first_data = false;
           }
-          umma_commit(&empty_bar[s]);
+          if (!(p.dbg & 16)) {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              // advance 32 bytes (16 fp16) along K inside the 128-byte swizzle atom: +2 in the (addr>>4) field
+              if (CG == 2) umma_f16_cg2_w(d_addr, dlo + 2 * k, dlo + (A_BYTES >> 4) + 2 * k, DESC_HI, idesc, acc);
+              else umma_f16_w(d_addr, dlo + 2 * k, dlo + (A_BYTES >> 4) + 2 * k, DESC_HI, idesc, acc);
+              acc = 1;
+            }
+          }
+          if (CG == 2) umma_commit_cg2(&empty_bar[s], cmask);
+          else umma_commit(&empty_bar[s]);
+          dlo += STAGE_BYTES >> 4;
+          if (++s == STAGES) {
+            s = 0;
+            ph ^= 1;
+            dlo = desc_lo0;
+          }
         }
-        umma_commit(&acc_full[ab]);
+        if (CG == 2) umma_commit_cg2(&acc_full[ab], cmask);
+        else umma_commit(&acc_full[ab]);
       }
       SDB_TR(5, clock64() - clk0);
     }
-  } else {
+    __syncwarp();
+  } else if (!p.csk && warp < B_WARP) {
     // epilogue warps 2..9 : TMEM lane group = warp % 4; the two warps of a lane group alternate chunks.
     // Latency plan: everything the fused epilogue reads from global memory is requested BEFORE the accumulator is
     // ready - bias (+ FiLM) of the tile's columns go to a shared-memory table, the residual rows of a chunk are
     // prefetched into registers one chunk ahead (the first one while the main loop still runs) - so the chunk loop is
     // TMEM load -> FMAs -> staging -> TMA store with no exposed L2 round trip.
     pdl_wait();   // residual / FiLM reads and all output writes come after the previous kernel has completed
-    const int ew = warp - 2;
-    const int lg = warp & 3;
-    const int par = ew >> 2;
-    const int et = threadIdx.x - 64;
-    uint8_t* stg = staging + ew * STG_WARP_BYTES;
     float* stage = reinterpret_cast<float*>(stg);  // scalar path: [32][33] floats
-    const bool geglu = (p.act == SDB_ACT_GEGLU) && !p.ws;
-    constexpr int HALF = BN / 2;
-    const int n_chunks = geglu ? HALF / 32 : BN / 32;
-    const int n_lim = geglu ? p.N / 2 : p.N;   // output columns that exist
-    const bool st32 = p.ws || p.out_f32;   // an fp32 tile is staged in some phase (output or split-K partial)
-    const bool st16 = p.out_f16 != nullptr;
-    // staging buffers per chunk parity: fp32 tiles 4 KB each; fp16 hi 2 KB + lo 2 KB each (fp32+fp16 together: single)
-    const bool dbl = !(st32 && st16);
-    const bool split_fast = p.ws && p.fast;   // raw fp32 partial planes; finished by splitk_epilogue_kernel
-    const bool use_tab = p.fast && !split_fast;
-    const bool pre_res = use_tab && !geglu && p.residual != nullptr;
-    uint32_t flip = 0;
+    const uint32_t acc_empty_lead = CG == 2 ? mapa_shared(smem_u32(&acc_empty[0]), lead) : 0u;
+    auto release_acc = [&](uint32_t ab) {   // accumulator fully read by this warp: hand it back to the (leader's) MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (CG == 2 && pr != 0) mbar_arrive_cluster(acc_empty_lead + 8u * ab);
+        else mbar_arrive(&acc_empty[ab]);
+      }
+    };
     uint32_t local = 0;
-    for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x, ++local) {
-      const int m_tile = tile % p.m_tiles;
-      const int rest = tile / p.m_tiles;
-      const int n_tile = rest % p.n_tiles;
-      const int split = rest / p.n_tiles;
+    for (int u = unit0; u < n_units; u += ustride, ++local) {
+      int m_tile, n_tile, split;
+      decode(u, m_tile, n_tile, split);
       const uint32_t ab = local & 1;
-      int my_row;
-      const int r_tile = lg * 32 + lane;
-      const bool my_valid = map_row(p, m_tile, r_tile, my_row);
-      const int my_sample = my_valid ? my_row / p.rows_per_sample : 0;
-      // store-box origin of this warp's 32 rows
-      int sx, sy, sn;
-      if (p.taps == 1) {
-        sx = m_tile * BM + lg * 32;
-        sy = 0;
-        sn = 0;
-      } else {
-        const int tx = m_tile % p.tiles_x;
-        const int t2 = m_tile / p.tiles_x;
-        const int r0 = lg * 32;
-        sx = tx * p.TW + r0 % p.TW;
-        sy = (t2 % p.tiles_y) * p.TH + (r0 / p.TW) % p.TH;
-        sn = (t2 / p.tiles_y) * p.TN + r0 / (p.TW * p.TH);
-      }
-      // ---- column table of this tile: bias (+ FiLM of the sample each row half belongs to)
-      if (use_tab) {
-        if (local > 0) asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");   // readers of the previous tile's table
-        for (int i = et; i < 2 * BN; i += 32 * EPI_WARPS) {
-          const int hsel = i / BN, cl = i - hsel * BN;
-          const int col = n_tile * BN + cl;
-          float t = 0.f;
-          if (col < p.N) {
-            if (p.bias) t = __ldg(p.bias + col);
-            if (p.film && p.film_table) {
-              int prow;
-              if (map_row(p, m_tile, hsel * 64, prow))
-                t += __ldg(p.film + static_cast<size_t>(prow / p.rows_per_sample) * p.ldf + col);
-            }
-          }
-          coltab[i] = t;
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
-      }
-      // residual rows of one 32-column chunk -> registers (row per thread, 128 contiguous bytes)
+      const EpiRows rw = rows_of(m_tile, lg);
+      if (use_tab) fill_coltab(m_tile, n_tile, local == 0);
       float4 rcur[8];
-      auto load_res = [&](int c, float4 (&r)[8]) {
-        const int oc = n_tile * BN + c * 32;
-        if (my_valid && oc < n_lim) {
-          const float4* rp = reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(my_row) * p.ldr + oc);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) r[q] = rp[q];
-        } else {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) r[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      };
-      if (pre_res && par < n_chunks) load_res(par, rcur);
+      if (pre_res && par < n_chunks) load_res(rw, n_tile, par, rcur);
 
       mbar_wait(&acc_full[ab], (local >> 1) & 1);
       tc_fence_after();
@@ -471,128 +781,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       const uint32_t taddr = tmem_d + ab * BN + (static_cast<uint32_t>(lg * 32) << 16);
       int last_c = -1;
       for (int c = par; c < n_chunks; c += 2) last_c = c;
-      if (last_c < 0) {  // BN = 32: the odd-parity warps own no chunk but still take part in the hand-off
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[ab]);
-      }
-      // ---- fused epilogue + staging + TMA store of one 32x32 chunk held in registers (row per thread)
-      auto emit = [&](float (&v)[32], int ocol0, bool fuse, bool raw_partial, const float4 (&res)[8]) {
-        if (fuse) {
-          // alpha * acc + (bias [+ FiLM]) from the tile's column table; all pointers are 16-byte aligned on this path
-          const float4* tp = reinterpret_cast<const float4*>(coltab + (lg >= 2 ? BN : 0) + (ocol0 - n_tile * BN));
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 t = tp[q];
-            v[4 * q] = fmaf(v[4 * q], p.alpha, t.x);
-            v[4 * q + 1] = fmaf(v[4 * q + 1], p.alpha, t.y);
-            v[4 * q + 2] = fmaf(v[4 * q + 2], p.alpha, t.z);
-            v[4 * q + 3] = fmaf(v[4 * q + 3], p.alpha, t.w);
-          }
-          if (p.film && !p.film_table) {   // rows of a tile half span several samples: FiLM per row from global
-            const float4* fp = reinterpret_cast<const float4*>(p.film + static_cast<size_t>(my_sample) * p.ldf + ocol0);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              float4 t = __ldg(fp + q);
-              v[4 * q] += t.x;
-              v[4 * q + 1] += t.y;
-              v[4 * q + 2] += t.z;
-              v[4 * q + 3] += t.w;
-            }
-          }
-          if (p.residual) {   // prefetched (zeros for rows outside the problem)
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              v[4 * q] += res[q].x;
-              v[4 * q + 1] += res[q].y;
-              v[4 * q + 2] += res[q].z;
-              v[4 * q + 3] += res[q].w;
-            }
-          }
-          if (p.act != SDB_ACT_NONE) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
-          }
-        }
-        const bool w32 = raw_partial || p.out_f32;
-        const bool w16 = !raw_partial && p.out_f16;
-        const bool w16lo = w16 && p.out_f16_lo;
-        // staging buffer for this chunk; make sure the TMA store that last read it has finished reading
-        const uint32_t bsel = dbl ? (flip & 1) : 0;
-        if (lane == 0) {
-          if (dbl) tma_store_wait_read<1>();
-          else tma_store_wait_read<0>();
-        }
-        __syncwarp();
-        uint8_t* s32 = stg + bsel * 4096;
-        uint8_t* s16 = st32 ? stg + 4096 : stg + bsel * 4096;
-        uint8_t* s16l = s16 + 2048;
-        if (w32) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<float4*>(s32 + lane * 128 + ((q ^ (lane & 7)) << 4)) =
-                make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        }
-        if (w16) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            __half2 h[4];
-            uint4 u, ul;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[8 * q + 2 * e], v[8 * q + 2 * e + 1]);
-            u.x = *reinterpret_cast<uint32_t*>(&h[0]);
-            u.y = *reinterpret_cast<uint32_t*>(&h[1]);
-            u.z = *reinterpret_cast<uint32_t*>(&h[2]);
-            u.w = *reinterpret_cast<uint32_t*>(&h[3]);
-            const uint32_t off = lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4);
-            *reinterpret_cast<uint4*>(s16 + off) = u;
-            if (w16lo) {
-              __half2 l[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float2 hf = __half22float2(h[e]);
-                l[e] = __floats2half2_rn(v[8 * q + 2 * e] - hf.x, v[8 * q + 2 * e + 1] - hf.y);
-              }
-              ul.x = *reinterpret_cast<uint32_t*>(&l[0]);
-              ul.y = *reinterpret_cast<uint32_t*>(&l[1]);
-              ul.z = *reinterpret_cast<uint32_t*>(&l[2]);
-              ul.w = *reinterpret_cast<uint32_t*>(&l[3]);
-              *reinterpret_cast<uint4*>(s16l + off) = ul;
-            }
-          }
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-          if (raw_partial) {
-            tma_store_5d(&tm.ows, s32, ocol0, sx, sy, sn, split);
-          } else {
-            if (w32) tma_store_5d(&tm.o32, s32, ocol0, sx, sy, sn, 0);
-            if (w16) tma_store_5d(&tm.o16, s16, ocol0, sx, sy, sn, 0);
-            if (w16lo) tma_store_5d(&tm.o16lo, s16l, ocol0, sx, sy, sn, 0);
-          }
-          tma_store_commit();
-        }
-        if (!raw_partial && p.stats && w32) {
-          // GroupNorm statistics of the value just produced: lane c folds column c of the staged 32x32 tile into the
-          // CTA's shared column sums (flushed once per tile with one fp64 global atomic per column)
-          const uint32_t vmask = __ballot_sync(0xffffffffu, my_valid);
-          float cs = 0.f, cq = 0.f;
-#pragma unroll
-          for (int r = 0; r < 32; ++r) {
-            if ((vmask >> r) & 1u) {
-              float x = *reinterpret_cast<const float*>(s32 + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4) + (lane & 3) * 4);
-              cs += x;
-              cq = fmaf(x, x, cq);
-            }
-          }
-          const int cl = ocol0 - n_tile * BN + lane;
-          colsum[(lg * BN + cl) * 2] = cs;
-          colsum[(lg * BN + cl) * 2 + 1] = cq;
-        }
-        ++flip;
-      };
-
+      if (last_c < 0) release_acc(ab);  // BN = 32: the odd-parity warps own no chunk but still take part in the hand-off
 #pragma unroll 1
       for (int c = par; c < n_chunks; c += 2) {
         float v[32];
@@ -615,85 +804,138 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         } else {
           uint32_t rr[32];
           tmem_ld32(taddr + c * 32, rr);
-          if (has_next) load_res(c + 2, rnxt);   // next chunk's residual rows: in flight across this chunk's work
+          if (has_next) load_res(rw, n_tile, c + 2, rnxt);   // next chunk's residual rows: in flight across this chunk's work
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
           ocol0 = n_tile * BN + c * 32;
         }
-        if (c == last_c) {  // accumulator fully read by this warp: hand the buffer back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[ab]);
-        }
+        if (c == last_c) release_acc(ab);
         if (!p.fast) {
           // scalar transposed path (row pitch not TMA-addressable); split-K partials are finished by
           // splitk_epilogue_kernel on this path
 #pragma unroll
           for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = v[j];
           __syncwarp();
-          drain_chunk(p, stage, lane, my_row, my_sample, my_valid, ocol0, geglu ? p.N / 2 : p.N, geglu ? 2 : (p.ws ? 1 : 0),
-                      split);
+          drain_chunk(p, stage, lane, rw.row, rw.sample, rw.valid, ocol0, geglu ? p.N / 2 : p.N,
+                      geglu ? 2 : (p.ws ? 1 : 0), split);
           __syncwarp();
           continue;
         }
-        if (ocol0 < n_lim) emit(v, ocol0, !geglu && !split_fast, split_fast, rcur);   // (columns past N: nothing to write)
+        if (ocol0 < n_lim) emit(v, ocol0, n_tile, split, rw, lg, !geglu && !split_fast, split_fast, rcur);
         if (has_next) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) rcur[q] = rnxt[q];
         }
       }
-      // ---- per-tile flush of the fused GroupNorm column sums (see emit)
-      if (p.stats && !p.ws) {
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");   // all smem column sums of this tile are in
-        const int halves = p.stats_halves;
-        for (int i = et; i < halves * BN; i += 32 * EPI_WARPS) {
-          const int hsel = i / BN, cl = i - hsel * BN;
-          const int col = n_tile * BN + cl;
-          const int r_probe = hsel * 64;   // first tile row of this half
-          int prow;
-          const bool pv = map_row(p, m_tile, r_probe, prow);
-          if (pv && col < p.N) {
-            const int sample = prow / p.rows_per_sample;
-            double* dst = p.stats + ((static_cast<size_t>(m_tile & (STAT_SLOTS - 1)) * p.n_samples + sample) * p.N + col) * 2;
-            float a, b;
-            if (halves == 2) {
-              a = colsum[((2 * hsel) * BN + cl) * 2] + colsum[((2 * hsel + 1) * BN + cl) * 2];
-              b = colsum[((2 * hsel) * BN + cl) * 2 + 1] + colsum[((2 * hsel + 1) * BN + cl) * 2 + 1];
-            } else {
-              a = (colsum[cl * 2] + colsum[(BN + cl) * 2]) + (colsum[(2 * BN + cl) * 2] + colsum[(3 * BN + cl) * 2]);
-              b = (colsum[cl * 2 + 1] + colsum[(BN + cl) * 2 + 1]) +
-                  (colsum[(2 * BN + cl) * 2 + 1] + colsum[(3 * BN + cl) * 2 + 1]);
-            }
-            atomicAdd(dst, static_cast<double>(a));
-            atomicAdd(dst + 1, static_cast<double>(b));
+      if (p.stats && !p.ws && !(p.dbg & 2)) flush_stats(m_tile, n_tile);
+    }
+  }
+
+  // ---------------------------------------------------------------- cluster split-K: exchange + owner epilogue
+  if (p.csk) {
+    // S K-slices of ONE tile sit in the tensor memories of the cluster's CTAs. Rows are scattered to their owner
+    // (K slice o owns lane groups [o * 4/S, (o+1) * 4/S) of its pair-rank's 128 rows) through distributed shared
+    // memory into the (now idle) stage ring; the owner sums the S partials in slice order and runs the fused epilogue.
+    const int S = p.splits;
+    const int lgs_per = 4 / S;
+    int m_tile = 0, n_tile = 0, split = 0;
+    decode(unit0, m_tile, n_tile, split);
+    const int n_tasks = lgs_per * n_chunks;   // (owned lane group, chunk) pairs; <= 2 per epilogue warp
+    EpiRows rw0{}, rw1{};
+    float4 r0[8], r1[8];
+    if (warp >= 2 && warp < B_WARP) {
+      pdl_wait();
+      fill_coltab(m_tile, n_tile, true);
+      if (ew < n_tasks) {
+        rw0 = rows_of(m_tile, csplit * lgs_per + ew / n_chunks);
+        if (p.residual) load_res(rw0, n_tile, ew % n_chunks, r0);
+      }
+      if (ew + 8 < n_tasks) {
+        rw1 = rows_of(m_tile, csplit * lgs_per + (ew + 8) / n_chunks);
+        if (p.residual) load_res(rw1, n_tile, (ew + 8) % n_chunks, r1);
+      }
+      mbar_wait(&acc_full[0], 0);   // this CTA's (pair's) MMAs have completed
+      tc_fence_after();
+      if (threadIdx.x == 64) SDB_TR(6, clock64() - clk0);
+    }
+    __syncwarp();
+    cluster_sync_all();   // every CTA of the cluster is past its main loop: the stage rings are free
+    if (warp >= 2 && warp < B_WARP) {
+      const int owner = lg / lgs_per, lgsub = lg - owner * lgs_per;
+      const uint32_t dst = mapa_shared(smem_u32(smem), static_cast<uint32_t>(owner * CG) + pr) +
+                           static_cast<uint32_t>((csplit * lgs_per + lgsub) * n_chunks) * 4096u + lane * 128u;
+      const uint32_t taddr = tmem_d + (static_cast<uint32_t>(lg * 32) << 16);
+#pragma unroll 1
+      for (int c = par; c < n_chunks; c += 2) {
+        uint32_t rr[32];
+        tmem_ld32(taddr + c * 32, rr);
+        tmem_ld_wait();
+        const uint32_t a = dst + static_cast<uint32_t>(c) * 4096u;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          st_cluster_f32x4(a + ((q ^ (lane & 7)) << 4), __uint_as_float(rr[4 * q]), __uint_as_float(rr[4 * q + 1]),
+                           __uint_as_float(rr[4 * q + 2]), __uint_as_float(rr[4 * q + 3]));
+      }
+      tc_fence_before();
+    }
+    __syncwarp();
+    cluster_sync_all();   // partials have landed (release / acquire at cluster scope)
+    if (warp >= 2 && warp < B_WARP) {
+#pragma unroll 1
+      for (int k = 0; k < 2; ++k) {
+        const int t = ew + 8 * k;
+        if (t >= n_tasks) break;
+        const int lgsub = t / n_chunks, c = t - lgsub * n_chunks;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        for (int src = 0; src < S; ++src) {   // fixed order: deterministic
+          const uint8_t* rp = smem + static_cast<size_t>((src * lgs_per + lgsub) * n_chunks + c) * 4096 + lane * 128;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 t4 = *reinterpret_cast<const float4*>(rp + ((q ^ (lane & 7)) << 4));
+            v[4 * q] += t4.x;
+            v[4 * q + 1] += t4.y;
+            v[4 * q + 2] += t4.z;
+            v[4 * q + 3] += t4.w;
           }
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");   // slots consumed before the next tile rewrites them
+        const int ocol0 = n_tile * BN + c * 32;
+        if (ocol0 < n_lim) emit(v, ocol0, n_tile, 0, k ? rw1 : rw0, csplit * lgs_per + lgsub, true, false, k ? r1 : r0);
       }
+      if (p.stats) flush_stats(m_tile, n_tile);
     }
+  }
+
+  if (warp >= 2 && warp < B_WARP) {
     // smem may be released once the bulk stores have READ it; their global writes complete with the grid
     if (lane == 0) tma_store_wait_read<0>();
-    tc_fence_before();
     if (threadIdx.x == 64) SDB_TR(7, clock64() - clk0);
   }
-  __syncthreads();
+  tc_fence_before();
+  __syncwarp();
+  if (clustered) cluster_sync_all();   // the peer's tensor-core reads of this CTA's shared memory / remote arrives are done
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_d, TMEM_COLS);
+    if (CG == 2) tmem_dealloc_cg2(tmem_d, TMEM_COLS);
+    else tmem_dealloc(tmem_d, TMEM_COLS);
   }
   if (threadIdx.x == 0) SDB_TR(1, gtimer());
 }
 
-// split-K second pass: sum the fp32 partial planes and apply the fused epilogue. Block = 32 rows x 128 columns
-// (thread: 4 adjacent columns of rows ty, ty+8, ty+16, ty+24), so the GroupNorm column sums of the result fold
-// through shared memory into one fp64 atomic per column per block.
-__global__ void __launch_bounds__(256) splitk_epilogue_kernel(const GemmArgs p, int splits) {
-  __shared__ float red[8][128][2];
+// split-K second pass (workspace mode): sum the fp32 partial planes and apply the fused epilogue. Block = 32 rows x
+// (4 * CQ) columns (thread: 4 adjacent columns of rows ty, ty+8, ty+16, ty+24); the GroupNorm column sums of the
+// result fold through shared memory into per-(32-row block, channel group) partial entries (plain stores).
+template <int CQ>
+__global__ void __launch_bounds__(CQ * 8) splitk_epilogue_kernel(const GemmArgs p, int splits) {
+  constexpr int CB = CQ * 4;
+  __shared__ float red[8][CB][2];
   pdl_launch_dependents();
   pdl_wait();
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int col = blockIdx.x * 128 + tx * 4;
+  const int tx = threadIdx.x % CQ, ty = threadIdx.x / CQ;
+  const int col = blockIdx.x * CB + tx * 4;
   const size_t plane = static_cast<size_t>(p.M) * p.N;
   float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
   if (col < p.N) {
@@ -754,20 +996,22 @@ __global__ void __launch_bounds__(256) splitk_epilogue_kernel(const GemmArgs p, 
       red[ty][tx * 4 + j][1] = cq[j];
     }
     __syncthreads();
-    if (threadIdx.x < 128) {
-      const int c = blockIdx.x * 128 + threadIdx.x;
-      if (c < p.N && blockIdx.y * 32 < p.M) {
-        float a = 0.f, b = 0.f;
+    const int sg = p.stats_sg;
+    const int g = threadIdx.x;                       // channel group inside this column block (CB % sg == 0)
+    const int c0 = blockIdx.x * CB + g * sg;
+    const int row0 = blockIdx.y * 32;
+    if (g < CB / sg && c0 < p.N && row0 < p.M) {
+      float a = 0.f, b = 0.f;
+      for (int j = 0; j < sg; ++j) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          a += red[k][threadIdx.x][0];
-          b += red[k][threadIdx.x][1];
+          a += red[k][g * sg + j][0];
+          b += red[k][g * sg + j][1];
         }
-        const int sample = (blockIdx.y * 32) / p.rows_per_sample;
-        double* dst = p.stats + ((static_cast<size_t>(blockIdx.y & (STAT_SLOTS - 1)) * p.n_samples + sample) * p.N + c) * 2;
-        atomicAdd(dst, static_cast<double>(a));
-        atomicAdd(dst + 1, static_cast<double>(b));
       }
+      const int sample = row0 / p.rows_per_sample;
+      const int t = (row0 - sample * p.rows_per_sample) / 32;
+      p.stats[(static_cast<size_t>(sample) * p.stats_T + t) * (p.N / sg) + c0 / sg] = make_float2(a, b);
     }
   }
 }
@@ -786,21 +1030,20 @@ __global__ void __launch_bounds__(256) splitk_epilogue_scalar_kernel(const GemmA
   }
 }
 
-template <int BN>
-static int launch_gemm(const TmapPack& tm, const GemmArgs& p, cudaStream_t st) {
-  using Cfg = GemmCfg<BN>;
-  auto kern = gemm_tc_kernel<BN>;
-  static bool configured = false;
-  if (!configured) {
-    SDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-    configured = true;
-  }
-  const int tiles = p.m_tiles * p.n_tiles * p.splits;
-  const int grid = std::min(tiles, sm_count());
-  SDB_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM, st, tm, p));
-  SDB_LAUNCH_CHECK();
-  return 0;
-}
+// ------------------------------------------------------------------------------------------------ host side
+struct Choice {
+  int bn, cg, splits, csk;
+};
+
+struct Geometry {   // everything about a problem that does not depend on the tile choice
+  long M;
+  int k_iters, cpt;
+  long m_tiles;
+  int TW, TH, TN, tiles_x, tiles_y;
+  int rps;
+  bool geglu, want_stats, fast_possible;
+  int sg;
+};
 
 static int pow2_divisor(int v, int cap) {
   int p = 1;
@@ -808,56 +1051,246 @@ static int pow2_divisor(int v, int cap) {
   return p;
 }
 
-// Tile model used to pick (block_n, split-K). Per CTA the 64-wide K step of a 128 x bn tile moves (128 + bn) * 128 B
-// from L2 (the binding resource for 1-CTA tiles); the epilogue drains bn columns and, in the persistent kernel,
-// overlaps the next tile's main loop, so a tile costs max(mainloop, epilogue) plus a fixed hand-off. CTAs run in
-// waves of sm_count. Split-K adds an fp32 partial round trip and a second kernel.
-static double tile_cost(int n, long m_tiles, int k_iters, int bn, int splits, long M) {
-  long nt = (n + bn - 1) / bn;
-  long tiles = m_tiles * nt * splits;
-  long waves = (tiles + sm_count() - 1) / sm_count();
-  double mainloop = static_cast<double>((k_iters + splits - 1) / splits) * (128.0 + bn) * 1.6;
-  double epi = 10.0 * bn + 200.0;
-  double first = mainloop + epi;                       // first tile of a CTA cannot overlap
-  double steady = std::max(mainloop, epi) + 150.0;
-  double t = first + (waves - 1) * steady + 800.0;
-  if (splits > 1) t += 2500.0 + 6.0 * static_cast<double>(splits) * M * n / (sm_count() * 256.0);
+// Statistics slots per sample (0: this tile choice cannot produce fused statistics)
+static int stats_slots(const sdb_gemm_desc* d, const Geometry& g, const Choice& c, int* halves_out) {
+  int halves = 1;
+  if (g.sg <= 0 || d->n % g.sg != 0) return 0;
+  if (!g.fast_possible || !d->out_f32 || g.geglu) return 0;   // statistics come from the staged fp32 tile of the TMA-store path
+  if (c.splits > 1 && !c.csk) {   // workspace split-K: the second kernel produces them per 32-row block
+    if (g.rps % 32 != 0 || d->n % 4 != 0) return 0;
+    const int cb = (d->n % 160 == 0 && 160 % g.sg == 0) ? 160 : 128;
+    if (cb % g.sg != 0) return 0;
+    *halves_out = 1;
+    return g.rps / 32;
+  }
+  if (c.bn % g.sg != 0) return 0;
+  int T;
+  if (d->taps == 1) {
+    if (g.rps % 128 == 0) T = g.rps / 128;
+    else if (g.rps == 64) { T = 1; halves = 2; }
+    else return 0;
+  } else {
+    if (g.rps != d->h * d->w) return 0;
+    T = g.tiles_x * g.tiles_y;                                       // one slot per spatial tile position
+    if (g.TN == 1) halves = 1;                                       // TW * TH == 128: a tile lies inside one sample
+    else if (g.TW * g.TH == 64 && g.TN == 2) halves = 2;             // 64-pixel tiles of two consecutive samples
+    else return 0;
+  }
+  *halves_out = halves;
+  return c.csk ? T * c.splits : T;
+}
+
+static bool choice_valid(const sdb_gemm_desc* d, const Geometry& g, const Choice& c) {
+  if (!(c.bn == 32 || c.bn == 64 || c.bn == 128 || c.bn == 160 || c.bn == 256)) return false;
+  if (c.cg == 2 && (c.bn < 128 || g.m_tiles < 2)) return false;
+  if (g.geglu && (c.splits > 1 || (c.bn != 128 && c.bn != 256))) return false;
+  if (c.splits < 1 || c.splits > g.k_iters) return false;
+  if (c.csk) {
+    const int ips = (g.k_iters + c.splits - 1) / c.splits;
+    if ((g.k_iters + ips - 1) / ips != c.splits) return false;   // every CTA of the cluster needs a non-empty K slice
+    if (!(c.splits == 2 || c.splits == 4) || c.splits * c.cg > 8 || !g.fast_possible || g.geglu) return false;
+    if (g.k_iters / c.splits < 2) return false;
+  } else if (c.splits > 1) {
+    if (d->workspace == nullptr) return false;
+    if (d->workspace_floats > 0 && static_cast<long>(c.splits) * g.M * d->n > d->workspace_floats) return false;
+  }
+  if (g.want_stats) {
+    int h;
+    if (stats_slots(d, g, c, &h) == 0) return false;
+  }
+  return true;
+}
+
+// Tile model used to pick (block_n, CTA pair, split-K). These GEMMs are bound by L2 -> SM operand traffic (chip-wide
+// ~4600 B/clk, ~64 B/clk per SM), by the tensor pipe (2*bn clk per 64-deep K step of a 128-row CTA tile) and by fixed
+// per-launch cost; a CTA pair halves the B bytes per CTA, split-K keeps tiles large at small M.
+static double choice_cost(const sdb_gemm_desc* d, const Geometry& g, const Choice& c) {
+  const int sms = sm_count();
+  const long nt = (d->n + c.bn - 1) / c.bn;
+  const long m_units = (g.m_tiles + c.cg - 1) / c.cg;
+  const long units = m_units * nt * c.splits;            // CTA (pair) work items
+  const long ctas = units * c.cg;
+  const int iters = (g.k_iters + c.splits - 1) / c.splits;
+  const double stage_bytes = 16384.0 + (c.bn / c.cg) * 128.0;
+  long slots = c.csk ? std::max(1, sms / (c.splits * c.cg)) * (c.splits * c.cg) : (sms / c.cg) * c.cg;
+  const long rounds = (ctas + slots - 1) / slots;
+  const double cta_iters = static_cast<double>(iters) * rounds;
+  const double t_mma = cta_iters * 2.0 * c.bn;
+  const double t_l2_cta = cta_iters * stage_bytes / 64.0;
+  const double t_l2_chip = static_cast<double>(ctas) * iters * stage_bytes / 4600.0;
+  double t = std::max(t_mma, std::max(t_l2_cta, t_l2_chip));
+  t += 1800.0 + 14.0 * c.bn;                    // epilogue of the last tile (not overlapped)
+  t += 7000.0;                                  // launch, prologue, pipeline fill
+  if (c.csk) t += 2500.0 + 128.0 * c.bn * 4.0 * (c.splits - 1) / c.splits / 20.0;
+  else if (c.splits > 1) t += 14000.0 + 8.0 * c.splits * g.M * d->n / (sms * 256.0);
+  const long pad = nt * c.bn - d->n;             // zero-padded columns still cost MMA + B traffic
+  if (pad > 0) t *= 1.0 + 0.5 * static_cast<double>(pad) / (nt * c.bn);
   return t;
 }
 
-static void pick_tiles(int n, long m_tiles, int k_iters, long M, bool geglu, int fixed_bn, int fixed_splits,
-                       long ws_floats, int* bn_out, int* splits_out) {
-  const int cands[] = {256, 160, 128, 64, 32};
+static int make_geometry(const sdb_gemm_desc* d, Geometry* g) {
+  const void* srcs[MAX_SRC] = {d->a0, d->a1, d->a2, d->a3};
+  const int chans[MAX_SRC] = {d->c0, d->c1, d->c2, d->c3};
+  int nsrc = 0, chunks = 0;
+  for (int i = 0; i < MAX_SRC; ++i) {
+    if (srcs[i] == nullptr) break;
+    SDB_CHECK(chans[i] > 0 && chans[i] % 64 == 0, "sdb_gemm: channel count of source %d must be a positive multiple of 64 (got %d)",
+              i, chans[i]);
+    ++nsrc;
+    chunks += chans[i] / 64;
+  }
+  for (int i = nsrc; i < MAX_SRC; ++i)
+    SDB_CHECK(srcs[i] == nullptr && chans[i] == 0, "sdb_gemm: A sources must be contiguous (a%d/c%d)", i, i);
+  g->M = static_cast<long>(d->nb) * d->h * d->w;
+  SDB_CHECK(g->M < (1L << 31), "sdb_gemm: M too large");
+  g->cpt = chunks;
+  g->k_iters = d->taps * chunks;
+  g->geglu = d->act == SDB_ACT_GEGLU;
+  g->rps = d->rows_per_sample > 0 ? d->rows_per_sample : d->h * d->w;
+  if (d->taps == 1) {
+    g->TW = 128;
+    g->TH = 1;
+    g->TN = 1;
+    g->tiles_x = static_cast<int>((g->M + 127) / 128);
+    g->tiles_y = 1;
+    g->m_tiles = g->tiles_x;
+  } else {
+    g->TW = pow2_divisor(d->w, 128);
+    g->TH = pow2_divisor(d->h, 128 / g->TW);
+    g->TN = 128 / (g->TW * g->TH);
+    g->tiles_x = d->w / g->TW;
+    g->tiles_y = (d->h + g->TH - 1) / g->TH;
+    g->m_tiles = static_cast<long>(g->tiles_x) * g->tiles_y * ((d->nb + g->TN - 1) / g->TN);
+  }
+  g->want_stats = d->stats_out != nullptr;
+  g->sg = d->stats_group > 0 ? d->stats_group : 1;
+  const int n_out = g->geglu ? d->n / 2 : d->n;
+  const int ldo = d->ldo > 0 ? d->ldo : n_out;
+  const int ldf = d->ldf > 0 ? d->ldf : d->n;
+  const int ldr = d->ldr > 0 ? d->ldr : d->n;
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  g->fast_possible = (n_out % 32 == 0) && (ldo % 8 == 0) && (!d->bias || al16(d->bias)) &&
+                     (!d->film || (al16(d->film) && ldf % 4 == 0)) && (!d->residual || (al16(d->residual) && ldr % 4 == 0)) &&
+                     (!d->out_f32 || al16(d->out_f32)) && (!d->out_f16 || al16(d->out_f16)) &&
+                     (!d->out_f16_lo || al16(d->out_f16_lo));
+  return 0;
+}
+
+// Resolve (block_n, pair, split-K) for a problem: explicit requests of the descriptor are honoured, the rest is picked
+// by the tile model.
+static int resolve_choice(const sdb_gemm_desc* d, const Geometry& g, Choice* out) {
+  const int bns[] = {256, 160, 128, 64, 32};
+  const int sps[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32};
+  int want_splits = d->splits;                      // >1 explicit, 0/1 none, -1 auto
+  if (want_splits > g.k_iters) want_splits = g.k_iters;
+  Choice best{0, 1, 1, 0};
   double best_t = 1e300;
-  int best_bn = 128, best_s = 1;
-  for (int bn : cands) {
-    if (fixed_bn > 0 && bn != fixed_bn) continue;
-    if (geglu && bn != 128) continue;
-    if (fixed_bn <= 0 && bn > 32 && ((n + bn - 1) / bn) * bn - n >= bn / 2 && n > 32) continue;  // mostly padding
-    int smax = 1;
-    if (fixed_splits == -1 && !geglu) {
-      smax = k_iters / 4;
-      if (smax > 32) smax = 32;
-      if (smax < 1) smax = 1;
-    }
-    for (int s = 1; s <= smax; ++s) {
-      if (s > 1 && static_cast<long>(s) * M * n > ws_floats) break;
-      int sp = fixed_splits > 1 ? fixed_splits : s;
-      double t = tile_cost(n, m_tiles, k_iters, bn, sp, M);
-      if (t < best_t) {
-        best_t = t;
-        best_bn = bn;
-        best_s = sp;
+  for (int bn : bns) {
+    if (d->block_n > 0 && bn != d->block_n) continue;
+    if (g.geglu && d->block_n <= 0 && bn != 128) continue;    // GEGLU weights are packed per tile: 128 unless told
+    if (d->block_n <= 0 && bn > 32 && ((d->n + bn - 1) / bn) * bn - d->n >= bn / 2 && d->n > 32) continue;  // mostly padding
+    for (int cg = 1; cg <= 2; ++cg) {
+      if (d->pair == 1 && cg != 1) continue;
+      if (d->pair == 2 && cg != 2) continue;
+      for (int mode = 0; mode < 2; ++mode) {        // 0: workspace (or no) split-K, 1: cluster split-K
+        if (d->splitk_mode == 1 && mode == 1) continue;
+        if (d->splitk_mode == 2 && mode == 0 && want_splits != 0 && want_splits != 1 && want_splits != -1) continue;
+        for (int spi : sps) {
+          int sp = spi;
+          if (want_splits > 1) {      // explicit factor: try exactly that one
+            if (spi != 1) continue;
+            sp = want_splits;
+          }
+          if (mode == 1 && sp == 1) continue;
+          if ((want_splits == 0 || want_splits == 1) && sp != 1) continue;
+          Choice c{bn, cg, sp, mode};
+          if (!choice_valid(d, g, c)) continue;
+          const double t = choice_cost(d, g, c);
+          if (t < best_t) {
+            best_t = t;
+            best = c;
+          }
+        }
       }
     }
   }
-  *bn_out = best_bn;
-  *splits_out = best_s;
+  SDB_CHECK(best.bn != 0, "sdb_gemm: no valid tile configuration (block_n %d, pair %d, splits %d, mode %d%s)", d->block_n,
+            d->pair, d->splits, d->splitk_mode, g.want_stats ? ", fused statistics requested" : "");
+  *out = best;
+  return 0;
+}
+
+template <int BN, int CG, bool DEEP>
+static int launch_gemm_cfg(const TmapPack& tm, const GemmArgs& p, cudaStream_t st) {
+  using Cfg = GemmCfg<BN, CG, DEEP>;
+  auto kern = gemm_tc_kernel<BN, CG, DEEP>;
+  static bool configured = false;
+  if (!configured) {
+    SDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    configured = true;
+  }
+  const int units = p.m_units * p.n_tiles * p.splits;
+  int grid, cluster = 1;
+  if (p.csk) {
+    cluster = p.splits * CG;
+    grid = p.m_units * p.n_tiles * cluster;
+  } else {
+    cluster = CG;
+    grid = std::min(units, sm_count() / CG) * CG;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (cluster > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = cluster;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  SDB_CUDA(cudaLaunchKernelEx(&cfg, kern, tm, p));
+  SDB_LAUNCH_CHECK();
+  return 0;
+}
+
+// one tile per CTA (all of them resident at once, or cluster split-K) -> the deep-pipeline instantiation
+template <int BN, int CG>
+static int launch_gemm(const TmapPack& tm, const GemmArgs& p, cudaStream_t st) {
+  const int units = p.m_units * p.n_tiles * p.splits;
+  const bool deep = p.csk || units <= sm_count() / CG;
+  return deep ? launch_gemm_cfg<BN, CG, true>(tm, p, st) : launch_gemm_cfg<BN, CG, false>(tm, p, st);
 }
 
 }  // namespace sdb
 
 using namespace sdb;
+
+extern "C" int sdb_gemm_plan(const sdb_gemm_desc* d, int32_t* out) {
+  SDB_CHECK(d && out, "sdb_gemm_plan: null argument");
+  SDB_CHECK(d->taps == 1 || d->taps == 9, "sdb_gemm: taps must be 1 or 9 (got %d)", d->taps);
+  Geometry g;
+  if (make_geometry(d, &g)) return 1;
+  Choice c;
+  if (resolve_choice(d, g, &c)) return 1;
+  int halves = 1;
+  out[0] = c.bn;
+  out[1] = c.cg;
+  out[2] = c.splits;
+  out[3] = c.splits > 1 ? (c.csk ? 2 : 1) : 0;
+  out[4] = g.want_stats ? stats_slots(d, g, c, &halves) : 0;
+  return 0;
+}
 
 extern "C" int sdb_gemm(const sdb_gemm_desc* d, sdb_stream_t stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -865,30 +1298,35 @@ extern "C" int sdb_gemm(const sdb_gemm_desc* d, sdb_stream_t stream) {
   SDB_CHECK(d->taps == 1 || d->taps == 9, "sdb_gemm: taps must be 1 or 9 (got %d)", d->taps);
   const void* srcs[MAX_SRC] = {d->a0, d->a1, d->a2, d->a3};
   const int chans[MAX_SRC] = {d->c0, d->c1, d->c2, d->c3};
-  int nsrc = 0, ctot = 0;
-  for (int i = 0; i < MAX_SRC; ++i) {
-    if (srcs[i] == nullptr) break;
-    SDB_CHECK(chans[i] > 0 && chans[i] % 64 == 0, "sdb_gemm: channel count of source %d must be a positive multiple of 64 (got %d)",
-              i, chans[i]);
-    ++nsrc;
-    ctot += chans[i];
-  }
-  for (int i = nsrc; i < MAX_SRC; ++i)
-    SDB_CHECK(srcs[i] == nullptr && chans[i] == 0, "sdb_gemm: A sources must be contiguous (a%d/c%d)", i, i);
   SDB_CHECK(d->nb > 0 && d->h > 0 && d->w > 0 && d->n > 0, "sdb_gemm: bad dims");
   SDB_CHECK(d->out_f16 || d->out_f32, "sdb_gemm: no output");
   SDB_CHECK(!d->out_f16_lo || d->out_f16, "sdb_gemm: out_f16_lo needs out_f16");
-
-  GemmArgs p{};
   const int cstride = d->conv_stride > 1 ? d->conv_stride : 1;
   SDB_CHECK(cstride == 1 || (cstride == 2 && d->taps == 9), "sdb_gemm: conv_stride must be 1 or 2 (3x3 convs only)");
   SDB_CHECK(d->conv_shift == 0 || d->taps == 9, "sdb_gemm: conv_shift applies to 3x3 convs only");
   const int in_h = d->in_h > 0 ? d->in_h : d->h, in_w = d->in_w > 0 ? d->in_w : d->w;
   SDB_CHECK((in_h == d->h && in_w == d->w) || d->taps == 9, "sdb_gemm: in_h / in_w apply to 3x3 convs only");
-  p.cstride = cstride;
-  p.cshift = d->conv_shift;
-  const long M = static_cast<long>(d->nb) * d->h * d->w;
-  SDB_CHECK(M < (1L << 31), "sdb_gemm: M too large");
+  Geometry g;
+  if (make_geometry(d, &g)) return 1;
+  const bool geglu = g.geglu;
+  if (geglu) {
+    SDB_CHECK(d->n % 128 == 0, "sdb_gemm: GEGLU needs n %% 128 == 0");
+    SDB_CHECK(!d->film && !d->residual && d->splits <= 1, "sdb_gemm: GEGLU epilogue excludes film/residual/split-K");
+  }
+  if (g.want_stats)
+    SDB_CHECK(g.fast_possible && d->out_f32 && !geglu, "sdb_gemm: stats_out needs the TMA-store epilogue with an fp32 output");
+  Choice ch;
+  if (resolve_choice(d, g, &ch)) return 1;
+  const int bn = ch.bn, splits_req = ch.splits;
+  SDB_CHECK(!geglu || d->n % bn == 0, "sdb_gemm: GEGLU needs n %% block_n == 0");
+
+  GemmArgs p{};
+  int nsrc = 0, ctot = 0;
+  for (int i = 0; i < MAX_SRC && srcs[i]; ++i) {
+    ++nsrc;
+    ctot += chans[i];
+  }
+  const long M = g.M;
   p.M = static_cast<int>(M);
   p.N = d->n;
   p.taps = d->taps;
@@ -896,15 +1334,17 @@ extern "C" int sdb_gemm(const sdb_gemm_desc* d, sdb_stream_t stream) {
   p.cb[0] = 0;
   for (int i = 0; i < nsrc; ++i) p.cb[i + 1] = p.cb[i] + chans[i] / 64;
   for (int i = nsrc; i < MAX_SRC; ++i) p.cb[i + 1] = p.cb[nsrc];
-  p.k_iters = d->taps * p.cb[nsrc];
+  p.k_iters = g.k_iters;
   p.H = d->h;
   p.W = d->w;
   p.NB = d->nb;
+  p.cstride = cstride;
+  p.cshift = d->conv_shift;
   p.alpha = d->alpha == 0.f ? 1.f : d->alpha;
   p.bias = d->bias;
   p.film = d->film;
   p.ldf = d->ldf > 0 ? d->ldf : d->n;
-  p.rows_per_sample = d->rows_per_sample > 0 ? d->rows_per_sample : d->h * d->w;
+  p.rows_per_sample = g.rps;
   p.residual = d->residual;
   p.ldr = d->ldr > 0 ? d->ldr : d->n;
   p.out_f16 = static_cast<__half*>(d->out_f16);
@@ -912,43 +1352,23 @@ extern "C" int sdb_gemm(const sdb_gemm_desc* d, sdb_stream_t stream) {
   p.out_f32 = d->out_f32;
   p.act = d->act;
   p.b_static = d->b_dynamic ? 0 : 1;
-  const bool geglu = d->act == SDB_ACT_GEGLU;
   const int n_out = geglu ? d->n / 2 : d->n;
   p.ldo = d->ldo > 0 ? d->ldo : n_out;
-  if (geglu) {
-    SDB_CHECK(d->n % 128 == 0, "sdb_gemm: GEGLU needs n %% 128 == 0");
-    SDB_CHECK(!d->film && !d->residual && d->splits <= 1, "sdb_gemm: GEGLU epilogue excludes film/residual/split-K");
-  }
+  p.TW = g.TW;
+  p.TH = g.TH;
+  p.TN = g.TN;
+  p.tiles_x = g.tiles_x;
+  p.tiles_y = g.tiles_y;
+  const long m_tiles = g.m_tiles;
 
-  long m_tiles;
-  if (d->taps == 1) {
-    p.TW = 128;
-    p.TH = 1;
-    p.TN = 1;
-    p.tiles_x = static_cast<int>((M + 127) / 128);
-    p.tiles_y = 1;
-    m_tiles = p.tiles_x;
-  } else {
-    p.TW = pow2_divisor(d->w, 128);
-    p.TH = pow2_divisor(d->h, 128 / p.TW);
-    p.TN = 128 / (p.TW * p.TH);
-    p.tiles_x = d->w / p.TW;
-    p.tiles_y = (d->h + p.TH - 1) / p.TH;
-    m_tiles = static_cast<long>(p.tiles_x) * p.tiles_y * ((d->nb + p.TN - 1) / p.TN);
+  p.iters_per_split = (p.k_iters + splits_req - 1) / splits_req;
+  int splits = (p.k_iters + p.iters_per_split - 1) / p.iters_per_split;
+  p.csk = (ch.csk && splits == splits_req && splits > 1) ? 1 : 0;
+  if (ch.csk && !p.csk) {   // the K slices do not divide evenly enough: fall back to an unsplit launch
+    splits = 1;
+    p.iters_per_split = p.k_iters;
   }
-
-  int bn = 128, splits = 1;
-  {
-    int fixed_splits = d->splits;
-    if (fixed_splits == -1 && d->workspace == nullptr) fixed_splits = 0;
-    if (fixed_splits > p.k_iters) fixed_splits = p.k_iters;
-    pick_tiles(d->n, m_tiles, p.k_iters, M, geglu, d->block_n, fixed_splits, d->workspace_floats, &bn, &splits);
-  }
-  SDB_CHECK(bn == 32 || bn == 64 || bn == 128 || bn == 160 || bn == 256, "sdb_gemm: unsupported block_n %d", bn);
-  SDB_CHECK(!geglu || bn == 128, "sdb_gemm: GEGLU requires block_n 128");
-  p.iters_per_split = (p.k_iters + splits - 1) / splits;
-  splits = (p.k_iters + p.iters_per_split - 1) / p.iters_per_split;
-  if (splits > 1) {
+  if (splits > 1 && !p.csk) {
     SDB_CHECK(d->workspace != nullptr, "sdb_gemm: split-K needs a workspace");
     SDB_CHECK(d->workspace_floats <= 0 || static_cast<long>(splits) * M * d->n <= d->workspace_floats,
               "sdb_gemm: split-K workspace too small");
@@ -956,6 +1376,7 @@ extern "C" int sdb_gemm(const sdb_gemm_desc* d, sdb_stream_t stream) {
   }
   p.splits = splits;
   p.m_tiles = static_cast<int>(m_tiles);
+  p.m_units = static_cast<int>((m_tiles + ch.cg - 1) / ch.cg);
   p.n_tiles = (d->n + bn - 1) / bn;
   SDB_CHECK(m_tiles * p.n_tiles * splits < (1L << 30), "sdb_gemm: too many tiles");
 
@@ -988,16 +1409,14 @@ extern "C" int sdb_gemm(const sdb_gemm_desc* d, sdb_stream_t stream) {
     uint64_t K = static_cast<uint64_t>(d->taps) * ctot;
     uint64_t dims[2] = {K, static_cast<uint64_t>(d->n)};
     uint64_t str[1] = {K * 2};
-    uint32_t box[2] = {64, static_cast<uint32_t>(bn)};
+    uint32_t box[2] = {64, static_cast<uint32_t>(bn / ch.cg)};   // a CTA of a pair loads half of the weight tile
     if (make_tmap_f16(&tm.b, d->b, 2, dims, str, box)) return 1;
   }
   // output maps for the TMA-store epilogue (fast path); otherwise the scalar transposed path is used
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-  bool fast = (n_out % 32 == 0) && (p.ldo % 8 == 0) && (!p.bias || al16(p.bias)) &&
-              (!p.film || (al16(p.film) && p.ldf % 4 == 0)) && (!p.residual || (al16(p.residual) && p.ldr % 4 == 0)) &&
-              (!p.out_f32 || al16(p.out_f32)) && (!p.out_f16 || al16(p.out_f16)) &&
-              (!p.out_f16_lo || al16(p.out_f16_lo)) && (!p.ws || (d->n % 32 == 0 && al16(p.ws)));
+  bool fast = g.fast_possible && (!p.ws || (d->n % 32 == 0 && al16(p.ws)));
   p.fast = fast ? 1 : 0;
+  SDB_CHECK(!p.csk || fast, "sdb_gemm: cluster split-K needs the TMA-store epilogue");
   p.bw = d->taps == 1 ? 32 : std::min(p.TW, 32);
   p.bh = d->taps == 1 ? 1 : std::min(p.TH, 32 / p.bw);
   tm.o32 = tm.b;
@@ -1036,20 +1455,22 @@ extern "C" int sdb_gemm(const sdb_gemm_desc* d, sdb_stream_t stream) {
     if (p.out_f16 && make_out(&tm.o16, p.out_f16, 2, n_out, p.ldo, 1)) return 1;
     if (p.out_f16_lo && make_out(&tm.o16lo, p.out_f16_lo, 2, n_out, p.ldo, 1)) return 1;
   }
-  // fused GroupNorm statistics: per-(sample, channel) sums of the fp32 output, accumulated by the epilogue
+  // fused GroupNorm statistics: per-tile partial sums of the fp32 output, stored by the epilogue
   p.stats = nullptr;
   p.stats_halves = 1;
+  p.stats_sg = g.sg;
+  p.stats_tps = g.tiles_x * g.tiles_y;
   p.n_samples = static_cast<int>((M + p.rows_per_sample - 1) / p.rows_per_sample);
   if (d->stats_out) {
-    SDB_CHECK(fast && p.out_f32 && !geglu, "sdb_gemm: stats_out needs the TMA-store epilogue with an fp32 output");
-    SDB_CHECK(p.rows_per_sample % 64 == 0, "sdb_gemm: stats_out needs rows_per_sample %% 64 == 0 (got %d)",
-              p.rows_per_sample);
-    p.stats = static_cast<double*>(d->stats_out);
-    p.stats_halves = (p.rows_per_sample % 128 == 0) ? 1 : 2;
-    if (!d->stats_prezeroed)
-      SDB_CUDA(cudaMemsetAsync(p.stats, 0, static_cast<size_t>(STAT_SLOTS) * p.n_samples * d->n * 2 * sizeof(double), st));
+    Choice eff{bn, ch.cg, splits, p.csk};
+    int halves = 1;
+    const int T = stats_slots(d, g, eff, &halves);
+    SDB_CHECK(T > 0, "sdb_gemm: this problem / tile shape cannot produce fused statistics (rows_per_sample %d, block_n %d, group %d)",
+              p.rows_per_sample, bn, g.sg);
+    p.stats = static_cast<float2*>(d->stats_out);
+    p.stats_halves = halves;
+    p.stats_T = T;
   }
-
   // bias + FiLM fold into a per-tile column table when each 64-row half of every tile belongs to one sample
   p.film_table = 0;
   if (p.film) {
@@ -1057,20 +1478,41 @@ extern "C" int sdb_gemm(const sdb_gemm_desc* d, sdb_stream_t stream) {
     else p.film_table = (p.TW * p.TH >= 64 && p.rows_per_sample == d->h * d->w) ? 1 : 0;
   }
   p.trace = trace_slot(8 + 8 * 160);
-  int rc;
-  switch (bn) {
-    case 32: rc = launch_gemm<32>(tm, p, st); break;
-    case 64: rc = launch_gemm<64>(tm, p, st); break;
-    case 128: rc = launch_gemm<128>(tm, p, st); break;
-    case 160: rc = launch_gemm<160>(tm, p, st); break;
-    default: rc = launch_gemm<256>(tm, p, st); break;
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("SDB_DBG");
+      dbg = e ? atoi(e) : 0;
+    }
+    p.dbg = dbg;
+  }
+
+  int rc = 1;
+  if (ch.cg == 2) {
+    switch (bn) {
+      case 128: rc = launch_gemm<128, 2>(tm, p, st); break;
+      case 160: rc = launch_gemm<160, 2>(tm, p, st); break;
+      case 256: rc = launch_gemm<256, 2>(tm, p, st); break;
+      default: SDB_CHECK(false, "sdb_gemm: CTA pairs need block_n 128, 160 or 256 (got %d)", bn);
+    }
+  } else {
+    switch (bn) {
+      case 32: rc = launch_gemm<32, 1>(tm, p, st); break;
+      case 64: rc = launch_gemm<64, 1>(tm, p, st); break;
+      case 128: rc = launch_gemm<128, 1>(tm, p, st); break;
+      case 160: rc = launch_gemm<160, 1>(tm, p, st); break;
+      default: rc = launch_gemm<256, 1>(tm, p, st); break;
+    }
   }
   if (rc) return rc;
-  if (splits > 1) {
+  if (splits > 1 && !p.csk) {
     const bool vec = (p.N % 4 == 0) && (p.ldo % 4 == 0) && (!p.residual || p.ldr % 4 == 0) && (!p.film || p.ldf % 4 == 0);
     if (vec) {
-      dim3 grid((p.N + 127) / 128, (p.M + 31) / 32);
-      SDB_CUDA(launch_pdl(splitk_epilogue_kernel, grid, dim3(256), 0, st, p, splits));
+      const bool wide = p.N % 160 == 0 && 160 % p.stats_sg == 0;
+      const int cb = wide ? 160 : 128;
+      dim3 grid((p.N + cb - 1) / cb, (p.M + 31) / 32);
+      if (wide) SDB_CUDA(launch_pdl(splitk_epilogue_kernel<40>, grid, dim3(320), 0, st, p, splits));
+      else SDB_CUDA(launch_pdl(splitk_epilogue_kernel<32>, grid, dim3(256), 0, st, p, splits));
     } else {
       SDB_CHECK(!p.stats, "sdb_gemm: stats_out with split-K needs n %% 4 == 0");
       size_t total = static_cast<size_t>(p.M) * p.N;

@@ -123,6 +123,56 @@ __global__ void __launch_bounds__(GN_THREADS)
   }
 }
 
+// Fold of the per-tile statistics partials when a sample has many tile slots (large images: one slot per 128 output
+// pixels): grid = (groups, nb); a block sums every entry / slot of its group in a fixed thread-strided order (fp64),
+// tree-reduces and publishes mean / rstd, so the apply blocks read 8 bytes per group instead of the whole slot list.
+__global__ void __launch_bounds__(GN_THREADS)
+    gn_fold_kernel(const float2* __restrict__ cs0, int T0, const float2* __restrict__ cs1, int T1, int sg, int c0, int c1,
+                   int groups, int hw, float eps, float* __restrict__ meanrstd) {
+  __shared__ double ra[GN_THREADS / 32], rb[GN_THREADS / 32];
+  const int g = blockIdx.x, n = blockIdx.y;
+  const int C = c0 + c1, cpg = C / groups;
+  pdl_launch_dependents();
+  pdl_wait();
+  double a = 0.0, b = 0.0;
+  for (int c = g * cpg; c < (g + 1) * cpg; c += sg) {
+    const bool first = c < c0;
+    const float2* src = first ? cs0 : cs1;
+    const int T = first ? T0 : T1;
+    const int E = (first ? c0 : c1) / sg;
+    const int e = (first ? c : c - c0) / sg;
+    for (int t = threadIdx.x; t < T; t += GN_THREADS) {
+      const float2 v = src[(static_cast<size_t>(n) * T + t) * E + e];
+      a += static_cast<double>(v.x);
+      b += static_cast<double>(v.y);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    ra[threadIdx.x >> 5] = a;
+    rb[threadIdx.x >> 5] = b;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    a = 0.0;
+    b = 0.0;
+    for (int k = 0; k < GN_THREADS / 32; ++k) {
+      a += ra[k];
+      b += rb[k];
+    }
+    const double cnt = static_cast<double>(hw) * cpg;
+    const double m = a / cnt;
+    double v = b / cnt - m * m;
+    if (v < 0) v = 0;
+    meanrstd[(static_cast<size_t>(n) * groups + g) * 2] = static_cast<float>(m);
+    meanrstd[(static_cast<size_t>(n) * groups + g) * 2 + 1] = static_cast<float>(1.0 / sqrt(v + static_cast<double>(eps)));
+  }
+}
+
 // pass 2: normalise (+SiLU) -> fp16, optional raw fp16 cast. grid = (slabs, nb); dynamic smem: float2[C] per-channel
 // {scale, shift} so the streaming loop is one FMA (+ SiLU) per element. The element loop keeps four independent 16-byte
 // loads in flight per thread and walks (row, channel quad) incrementally (no integer division per element).
@@ -133,7 +183,7 @@ __global__ void __launch_bounds__(GN_THREADS)
                     int rows_per_block, const float* __restrict__ meanrstd, const float* __restrict__ gamma,
                     const float* __restrict__ beta, float eps, int silu, __half* __restrict__ out,
                     __half* __restrict__ raw, __half* __restrict__ out_lo, __half* __restrict__ raw_lo,
-                    const double* __restrict__ cs0, const double* __restrict__ cs1) {
+                    const float2* __restrict__ cs0, int T0, const float2* __restrict__ cs1, int T1, int sg) {
   extern __shared__ float2 gn_ab[];   // [C] {rstd * gamma, beta - mean * rstd * gamma}
   const int C = c0 + c1;
   const int cpg = C / groups;
@@ -142,20 +192,22 @@ __global__ void __launch_bounds__(GN_THREADS)
   pdl_launch_dependents();
   pdl_wait();
   if (cs0) {
-    // per-channel {sum, sum of squares} accumulated by the producing GEMM epilogues (sdb_gemm.stats_out): fold the
-    // channels of each group (8 lanes per group) in fp64
+    // per-tile partial {sum, sum of squares} per sg-channel entry, stored by the producing GEMM epilogues
+    // (sdb_gemm.stats_out, [sample][T][C / sg]): fold the entries and tile slots of each group in a fixed order, fp64
+    // (8 lanes per group, then a butterfly: the result does not depend on scheduling)
     const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;
     if (g < groups) {
       double a = 0.0, b = 0.0;
-      for (int c = g * cpg + sub; c < (g + 1) * cpg; c += 8) {
-        // the producers spread their atomics over 4 accumulator copies [slot][nb][c][2]
-#pragma unroll
-        for (int slot = 0; slot < 4; ++slot) {
-          const double* q = c < c0 ? cs0 + ((static_cast<size_t>(slot) * gridDim.y + n) * c0 + c) * 2
-                                   : cs1 + ((static_cast<size_t>(slot) * gridDim.y + n) * c1 + (c - c0)) * 2;
-          const double2 v = *reinterpret_cast<const double2*>(q);
-          a += v.x;
-          b += v.y;
+      for (int c = g * cpg; c < (g + 1) * cpg; c += sg) {
+        const bool first = c < c0;
+        const float2* src = first ? cs0 : cs1;
+        const int T = first ? T0 : T1;
+        const int E = (first ? c0 : c1) / sg;
+        const int e = (first ? c : c - c0) / sg;
+        for (int t = sub; t < T; t += 8) {
+          const float2 v = src[(static_cast<size_t>(n) * T + t) * E + e];
+          a += static_cast<double>(v.x);
+          b += static_cast<double>(v.y);
         }
       }
 #pragma unroll
@@ -378,7 +430,8 @@ using namespace sdb;
 extern "C" int sdb_groupnorm(const float* x0, const float* x1, int32_t c0, int32_t c1, int32_t nb, int32_t hw,
                              int32_t groups, const float* gamma, const float* beta, float eps, int32_t silu,
                              void* out_f16, void* raw_f16, void* out_lo_f16, void* raw_lo_f16, void* stats_ws,
-                             const void* chan_stats0, const void* chan_stats1, sdb_stream_t stream) {
+                             const void* chan_stats0, const void* chan_stats1, int32_t stats_t0, int32_t stats_t1,
+                             int32_t stats_group, sdb_stream_t stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int C = c0 + c1;
   SDB_CHECK(x0 && out_f16 && stats_ws && gamma && beta, "sdb_groupnorm: null pointer");
@@ -390,7 +443,12 @@ extern "C" int sdb_groupnorm(const float* x0, const float* x1, int32_t c0, int32
   float* partial = static_cast<float*>(stats_ws);
   float* meanrstd = partial + static_cast<size_t>(nb) * GN_MAX_SLABS * groups * 2;
   unsigned int* counter = reinterpret_cast<unsigned int*>(meanrstd + static_cast<size_t>(nb) * groups * 2);
+  const int sg = stats_group > 0 ? stats_group : 1;
   const bool fused_stats = chan_stats0 != nullptr && (c1 == 0 || chan_stats1 != nullptr) && groups <= 32;
+  if (fused_stats)
+    SDB_CHECK(stats_t0 > 0 && (c1 == 0 || stats_t1 > 0) && (C / groups) % sg == 0 && c0 % sg == 0 && c1 % sg == 0,
+              "sdb_groupnorm: statistics entries of %d channels do not tile the groups (C %d + %d, %d groups)", sg, c0, c1,
+              groups);
   if (!fused_stats) SDB_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int) * nb, st));
   SDB_CHECK(!raw_lo_f16 || raw_f16, "sdb_groupnorm: raw_lo needs raw");
   // channel-lane width: threads of a block cover cw channels x (256 / cw) rows at a time
@@ -407,9 +465,18 @@ extern "C" int sdb_groupnorm(const float* x0, const float* x1, int32_t c0, int32
                                                                       eps, partial, counter, meanrstd);
     SDB_LAUNCH_CHECK();
   }
-  // apply: about two resident blocks per SM (each re-derives the group statistics, so fewer / fatter blocks), down to
+  // many tile slots per sample (large images): fold them once, the apply blocks then read mean / rstd
+  bool in_kernel_fold = fused_stats;
+  if (fused_stats && static_cast<long>(std::max(stats_t0, stats_t1)) * ((C / groups) / sg) > 512) {
+    SDB_CUDA(launch_pdl(gn_fold_kernel, dim3(groups, nb), dim3(GN_THREADS), 0, st, static_cast<const float2*>(chan_stats0),
+                        static_cast<int>(stats_t0), static_cast<const float2*>(chan_stats1), static_cast<int>(stats_t1), sg,
+                        c0, c1, groups, hw, eps, meanrstd));
+    SDB_LAUNCH_CHECK();
+    in_kernel_fold = false;
+  }
+  // apply: about four resident blocks per SM (each re-derives the group statistics from a few KB of partials), down to
   // one row per block at small resolutions
-  int aslabs = std::max(1, std::min(hw, (sm_count() * 2 + nb - 1) / nb));
+  int aslabs = std::max(1, std::min(hw, (sm_count() * 4 + nb - 1) / nb));
   int arows = (hw + aslabs - 1) / aslabs;
   aslabs = (hw + arows - 1) / arows;
   dim3 agrid(aslabs, nb);
@@ -418,8 +485,8 @@ extern "C" int sdb_groupnorm(const float* x0, const float* x1, int32_t c0, int32
                       static_cast<const float*>(meanrstd), gamma, beta, eps, silu, static_cast<__half*>(out_f16),
                       static_cast<__half*>(raw_f16), static_cast<__half*>(out_lo_f16),
                       static_cast<__half*>(raw_lo_f16),
-                      fused_stats ? static_cast<const double*>(chan_stats0) : static_cast<const double*>(nullptr),
-                      static_cast<const double*>(chan_stats1)));
+                      in_kernel_fold ? static_cast<const float2*>(chan_stats0) : static_cast<const float2*>(nullptr),
+                      static_cast<int>(stats_t0), static_cast<const float2*>(chan_stats1), static_cast<int>(stats_t1), sg));
   SDB_LAUNCH_CHECK();
   return 0;
 }

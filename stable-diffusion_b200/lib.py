@@ -44,6 +44,9 @@ class GemmDesc(C.Structure):
         ("conv_shift", C.c_int32),
         ("in_h", C.c_int32),
         ("in_w", C.c_int32),
+        ("pair", C.c_int32),
+        ("splitk_mode", C.c_int32),
+        ("stats_group", C.c_int32),
     ]
 
 
@@ -69,8 +72,9 @@ SIGNATURES = {
     "sdb_launch_count": ([], C.c_longlong),
     "sdb_debug_trace": ([_P, _L], C.c_longlong),
     "sdb_gemm": ([C.POINTER(GemmDesc), _P], C.c_int),
+    "sdb_gemm_plan": ([C.POINTER(GemmDesc), C.POINTER(C.c_int32)], C.c_int),
     "sdb_attention": ([C.POINTER(AttnDesc), _P], C.c_int),
-    "sdb_groupnorm": ([_P, _P, _I, _I, _I, _I, _I, _P, _P, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P], C.c_int),
+    "sdb_groupnorm": ([_P, _P, _I, _I, _I, _I, _I, _P, _P, _F, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P], C.c_int),
     "sdb_layernorm": ([_P, _I, _I, _P, _P, _F, _P, _P, _P], C.c_int),
     "sdb_softmax_rows": ([_P, _I, _I, _F, _P, _P], C.c_int),
     "sdb_nchw_to_nhwc": ([_P, _I, _I, _I, _P, _P, _P], C.c_int),

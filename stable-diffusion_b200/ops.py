@@ -56,14 +56,17 @@ def _chk32(t, name):
 def gemm(a0, b, *, a1=None, a2=None, a3=None, nb=None, h=None, w=None, taps=1, bias=None, film=None,
          rows_per_sample=0, residual=None, act=ACT_NONE, alpha=1.0, out_f16=None, out_f32=None, out_f16_lo=None,
          want_f16=False, want_f32=False, want_lo=False, n=None, block_n=0, splits=0, workspace=None,
-         want_stats=False, b_dynamic=False, conv_stride=1, conv_shift=0):
+         want_stats=False, stats_group=1, b_dynamic=False, conv_stride=1, conv_shift=0, pair=0, splitk_mode=0):
     """acc = A @ B^T with fused epilogue (see sdb_gemm in include/sdb200.h).
 
     a0 (, a1, a2, a3): fp16 [..., c_i] NHWC activations or plain [rows, c_i] matrices, concatenated along K.
     b: fp16 [n, taps*sum(c_i)].
     Returns (out_f16, out_f32), or (out_f16, out_f32, out_f16_lo) when the hi/lo pair is requested.
-    want_stats: the epilogue also accumulates the GroupNorm statistics of the fp32 output; they are attached to the
-    output tensor (see channel_stats()) so the following groupnorm() skips its reduction pass.
+    block_n / pair / splits / splitk_mode: explicit tile width, CTA pairs (2) or single CTAs (1), split-K factor and how
+    its partials meet (1 workspace + second kernel, 2 thread-block cluster); 0 = let the library (or the autotuner) pick.
+    want_stats: the epilogue also stores per-tile GroupNorm partial sums of the fp32 output (entries of `stats_group`
+    channels); they are attached to the output tensor (see channel_stats()) so the following groupnorm() skips its
+    reduction pass.
     """
     _chk16(a0, "a0")
     _chk16(b, "b")
@@ -97,6 +100,7 @@ def gemm(a0, b, *, a1=None, a2=None, a3=None, nb=None, h=None, w=None, taps=1, b
     if out_f32 is None and want_f32:
         out_f32 = torch.empty((M, n_out), dtype=torch.float32, device=a0.device)
     assert out_f16 is not None or out_f32 is not None
+    lib = _l.load()
     d = GemmDesc()
     ptrs = [_ptr(t_) for t_ in srcs] + [None] * (4 - len(srcs))
     cs = chans + [0] * (4 - len(chans))
@@ -113,62 +117,73 @@ def gemm(a0, b, *, a1=None, a2=None, a3=None, nb=None, h=None, w=None, taps=1, b
     d.act = act
     d.out_f16, d.out_f32, d.out_f16_lo = _ptr(out_f16), _ptr(out_f32), _ptr(out_f16_lo)
     d.ldo = 0
-    d.block_n = block_n
+    d.block_n, d.pair, d.splitk_mode = block_n, pair, splitk_mode
     d.b_dynamic = 1 if b_dynamic else 0   # b produced by the previous kernel: no early (pre-dependency) prefetch
     d.conv_stride, d.conv_shift, d.in_h, d.in_w = conv_stride, conv_shift, in_h, in_w
-    stats = None
-    if want_stats and out_f32 is not None and act != ACT_GEGLU and (taps == 9 or rows_per_sample):
-        rps = rows_per_sample if rows_per_sample else h * w
-        if rps % 64 == 0 and n % 32 == 0 and M % rps == 0:
-            stats = ARENA.take((4, M // rps, n, 2)) if ARENA is not None else None
-            if stats is not None:
-                d.stats_prezeroed = 1
-            else:
-                stats = torch.empty((4, M // rps, n, 2), dtype=torch.float64, device=a0.device)
-            d.stats_out = _ptr(stats)
-            out_f32._sdb_stats = stats   # travels with the tensor object (and, through ._base, with its views)
     d.splits = splits
-    if splits and (splits > 1 or splits == -1):
+    if splits and (splits > 1 or splits == -1) and splitk_mode != 2:
         if workspace is None:
             workspace = splitk_workspace(a0.device)
-        assert splits == -1 or workspace.numel() >= splits * M * n
         d.workspace = _ptr(workspace)
         d.workspace_floats = workspace.numel()
-    if block_n == 0 and splits in (0, -1) and act != ACT_GEGLU:
+    rps = rows_per_sample if rows_per_sample else h * w
+    stats_ok = want_stats and out_f32 is not None and act != ACT_GEGLU and (taps == 9 or rows_per_sample) and \
+        M % rps == 0 and n % stats_group == 0
+    d.stats_group = stats_group
+    if stats_ok:
+        d.stats_out = C.c_void_p(16)     # placeholder: the plan only needs to know that statistics are wanted
+    plan = (C.c_int32 * 5)()
+    tunable = block_n == 0 and pair == 0 and splitk_mode == 0 and splits in (0, -1) and act != ACT_GEGLU
+    if tunable:
         key = (M, n, b.shape[1], taps, len(srcs), bias is not None, film is not None, residual is not None, act,
-               out_f16 is not None, out_f32 is not None, out_f16_lo is not None, stats is not None, conv_stride)
+               out_f16 is not None, out_f32 is not None, out_f16_lo is not None, stats_ok, stats_group, conv_stride)
         choice = TUNED.get(key)
         if choice is None and AUTOTUNE:
-            choice = TUNED[key] = _tune_gemm(d, M, n, b.shape[1] // 64)
+            choice = TUNED[key] = _tune_gemm(d, M, n, rps, stats_ok, stats_group)
         if choice is not None:
-            d.block_n, d.splits = choice
+            d.block_n, d.pair, d.splits, d.splitk_mode = choice
+    rc = lib.sdb_gemm_plan(C.byref(d), plan)
+    if rc != 0 and stats_ok:             # this problem / tile shape cannot produce fused statistics: plain GEMM, the
+        stats_ok = False                 # consumer falls back to its own reduction pass
+        d.stats_out = None
+        rc = lib.sdb_gemm_plan(C.byref(d), plan)
+    _l.check(rc, "sdb_gemm_plan")
+    d.block_n, d.pair, d.splits, d.splitk_mode = plan[0], plan[1], plan[2], plan[3]
+    stats = None
+    if stats_ok:
+        shape = (M // rps, plan[4], n // stats_group, 2)
+        stats = ARENA.take(shape) if ARENA is not None else None
+        if stats is None:
+            stats = torch.empty(shape, dtype=torch.float32, device=a0.device)
+        d.stats_out = _ptr(stats)
+        out_f32._sdb_stats = (stats, plan[4], stats_group)   # travels with the tensor object (and, through ._base, its views)
     if RECORD is not None:
         # operand-split passes ([A_hi|A_lo|A_hi]) are overhead, not algorithmic work: count K once
         k_alg = b.shape[1] // 3 if (len(srcs) == 3 and srcs[0] is srcs[2]) else b.shape[1]
-        RECORD.append((d, 2.0 * M * n * k_alg, (srcs, b, bias, film, residual, out_f16, out_f32, out_f16_lo, workspace)))
+        RECORD.append((d, 2.0 * M * n * k_alg, (srcs, b, bias, film, residual, out_f16, out_f32, out_f16_lo, workspace, stats)))
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    _l.check(_l.load().sdb_gemm(C.byref(d), _stream()), "sdb_gemm")
+    _l.check(lib.sdb_gemm(C.byref(d), _stream()), "sdb_gemm")
     if PROFILE is not None:
         e1.record()
         PROFILE.append(("gemm", 2.0 * M * n * b.shape[1], e0, e1, (M, n, b.shape[1], taps)))
-    _count(2 if splits and splits > 1 else 1)
+    _count(2 if plan[3] == 1 else 1)
     if out_f16_lo is not None:
         return out_f16, out_f32, out_f16_lo
     return out_f16, out_f32
 
 
 class StatsArena:
-    """One pre-zeroed fp64 buffer per forward pass for all fused GroupNorm statistics (a single memset instead of one
-    per GEMM). reset() zeroes it and rewinds the bump pointer; gemm(want_stats=True) carves its [4, nb, n, 2] slice."""
+    """One fp32 bump buffer per forward pass for all fused GroupNorm statistics. The GEMM epilogues STORE their per-tile
+    partial sums (every slot has exactly one writer), so nothing is zeroed: reset() only rewinds the bump pointer;
+    gemm(want_stats=True) carves its [samples, T, n / group, 2] slice."""
 
-    def __init__(self, device, n_doubles=2 * 1024 * 1024):
-        self.buf = torch.zeros(n_doubles, dtype=torch.float64, device=device)
+    def __init__(self, device, n_floats=4 * 1024 * 1024):
+        self.buf = torch.empty(n_floats, dtype=torch.float32, device=device)
         self.off = 0
 
     def reset(self):
-        self.buf.zero_()
         self.off = 0
 
     def take(self, shape):
@@ -178,7 +193,7 @@ class StatsArena:
         if self.off + n > self.buf.numel():
             return None
         v = self.buf[self.off: self.off + n].view(shape)
-        self.off += (n + 1) // 2 * 2
+        self.off += (n + 3) // 4 * 4
         return v
 
 
@@ -186,34 +201,48 @@ ARENA = None   # set by the model around a forward pass (UNetModel._forward_impl
 
 
 def channel_stats(x):
-    """Fused GroupNorm statistics attached to `x` (or the tensor it is a view of) by the gemm() that produced it."""
+    """Fused GroupNorm statistics (partials tensor, slots per sample, channels per entry) attached to `x` (or the tensor
+    it is a view of) by the gemm() that produced it."""
     st = getattr(x, "_sdb_stats", None)
     if st is None and x._base is not None and x._base.numel() == x.numel():
         st = getattr(x._base, "_sdb_stats", None)
     return st
 
 
-def _tune_gemm(d, M, n, k_iters):
-    """Time the tile-width / split-K candidates of one GEMM problem on its real operands (CUDA events, GPU kept busy by
-    a leading spin so host launch gaps do not enter) and return the fastest (block_n, splits)."""
+def _tune_gemm(d, M, n, rps, stats_ok, stats_group):
+    """Time the (tile width, CTA pair, split-K) candidates of one GEMM problem on its real operands (CUDA events, GPU
+    kept busy by a leading spin so host launch gaps do not enter) and return the fastest
+    (block_n, pair, splits, splitk_mode)."""
     lib = _l.load()
     st = _stream()
+    keep = (d.block_n, d.pair, d.splits, d.splitk_mode, d.stats_out)
+    scratch = None
+    if stats_ok:   # large enough for any candidate's slot count (<= one slot per 32 rows)
+        scratch = torch.empty((M // rps) * max(1, rps // 32) * (n // stats_group) * 2 + 16, dtype=torch.float32,
+                              device=torch.device("cuda", torch.cuda.current_device()))
+        d.stats_out = _ptr(scratch)
+    plan = (C.c_int32 * 5)()
     cands = []
     for bn in (64, 128, 160, 256):
         pad = (n + bn - 1) // bn * bn - n
         if bn > 64 and pad >= bn // 2:
             continue
-        for sp in (1, 2, 3, 4, 6, 8, 12, 16, 24, 32):
-            if sp > 1 and (k_iters // sp < 2 or sp * M * n > d.workspace_floats):
-                continue
-            tiles = ((M + 127) // 128) * ((n + bn - 1) // bn) * sp
-            if sp > 1 and tiles > 3 * 148:
-                continue
-            cands.append((bn, sp))
-    best, best_t = (0, -1), float("inf")
-    keep = (d.block_n, d.splits)
-    for bn, sp in cands:
-        d.block_n, d.splits = bn, sp
+        for cg in (1, 2):
+            for sp, mode in ((1, 0), (2, 2), (4, 2), (2, 1), (3, 1), (4, 1), (6, 1), (8, 1), (12, 1), (16, 1)):
+                if mode == 1 and not d.workspace:
+                    continue
+                tiles = ((M + 127) // 128) * ((n + bn - 1) // bn) * sp
+                if sp > 1 and tiles > 3 * 148:
+                    continue
+                d.block_n, d.pair, d.splits, d.splitk_mode = bn, cg, sp, mode
+                if lib.sdb_gemm_plan(C.byref(d), plan) != 0:
+                    continue
+                if (plan[0], plan[1], plan[2], plan[3]) != (bn, cg, sp, mode if sp > 1 else 0):
+                    continue
+                cands.append((bn, cg, sp, mode))
+    best, best_t = None, float("inf")
+    for cand in cands:
+        d.block_n, d.pair, d.splits, d.splitk_mode = cand
         if lib.sdb_gemm(C.byref(d), st) != 0:      # warm-up / validity
             continue
         t = float("inf")
@@ -227,8 +256,9 @@ def _tune_gemm(d, M, n, k_iters):
             e1.synchronize()
             t = min(t, e0.elapsed_time(e1))
         if t < best_t:
-            best, best_t = (bn, sp), t
-    d.block_n, d.splits = keep
+            best, best_t = cand, t
+    d.block_n, d.pair, d.splits, d.splitk_mode, d.stats_out = keep
+    del scratch
     return best
 
 
@@ -286,12 +316,16 @@ def groupnorm(x0, gamma, beta, *, x1=None, groups=32, eps=1e-5, silu=False, want
     ws = torch.empty(nb * (128 * groups * 2 + groups * 2 + 1), dtype=torch.float32, device=x0.device)
     cs0 = channel_stats(x0)
     cs1 = channel_stats(x1) if x1 is not None else None
-    if cs0 is None or (x1 is not None and cs1 is None):
-        cs0 = cs1 = None
+    sg = cs0[2] if cs0 is not None else 1
+    cpg = (c0 + c1) // groups
+    if cs0 is None or (x1 is not None and (cs1 is None or cs1[2] != sg)) or cpg % sg or c0 % sg or c1 % sg:
+        cs0 = cs1 = None     # no (compatible) fused statistics: the kernel pair below computes them
+    t0, t1 = (cs0[1] if cs0 else 0), (cs1[1] if cs1 else 0)
     _l.check(_l.load().sdb_groupnorm(_ptr(x0), _ptr(x1), c0, c1, nb, h * w, groups, _ptr(gamma), _ptr(beta),
                                      eps, 1 if silu else 0, _ptr(out), _ptr(raw), _ptr(out_lo), _ptr(raw_lo), _ptr(ws),
-                                     _ptr(cs0), _ptr(cs1), _stream()), "sdb_groupnorm")
-    _count(3)
+                                     _ptr(cs0[0]) if cs0 else None, _ptr(cs1[0]) if cs1 else None, t0, t1, sg,
+                                     _stream()), "sdb_groupnorm")
+    _count(1 if cs0 else 3)
     if want_lo or want_raw_lo:
         return out, raw, out_lo, raw_lo
     return out, raw

@@ -58,10 +58,17 @@ def _pack_hilo_conv3(w):  # [N, C, 3, 3] fp32 -> [N, 9 * 3C], per tap [W_hi | W_
     return torch.cat([hi, hi, lo], dim=2).reshape(w.shape[0], -1).contiguous()
 
 
-def _pack_geglu(w, b):  # [8C, C]: rows [0,4C) value, [4C,8C) gate -> per 128-row tile [64 value | 64 gate]
+def _geglu_tile(inner):
+    """Accumulator tile width of the GEGLU GEMM: 256 ([128 value | 128 gate], CTA-pair tiles) when the inner width
+    allows, else 128."""
+    return 256 if inner % 128 == 0 else 128
+
+
+def _pack_geglu(w, b):  # [8C, C]: rows [0,4C) value, [4C,8C) gate -> per accumulator tile [half value | half gate]
     inner = w.shape[0] // 2
-    assert inner % 64 == 0
-    idx = torch.arange(inner, device=w.device).reshape(-1, 64)
+    half = _geglu_tile(inner) // 2
+    assert inner % half == 0
+    idx = torch.arange(inner, device=w.device).reshape(-1, half)
     perm = torch.cat([idx, idx + inner], dim=1).reshape(-1)
     return w[perm].contiguous().half(), b[perm].contiguous().float()
 
@@ -108,6 +115,9 @@ class UNetModel(nn.Module):
         self.plan = unet_plan(self.cfg)
         self.shapes = unet_param_shapes(self.cfg)
         self.precision = self.PRECISION
+        # channels per fused GroupNorm-statistics entry: every channel count of the UNet (and of its skip concats) is a
+        # multiple of model_channels, so the 32 groups always tile into entries of model_channels / 32 channels
+        self._sg = model_channels // 32 if model_channels % 32 == 0 else 1
         self.W = None           # packed weights (device)
         self._ctx_ref = None    # the context tensor whose cross-attention K/V are cached (strong reference)
         self._ctx_ver = -1
@@ -248,7 +258,7 @@ class UNetModel(nn.Module):
         else:
             hn, raw = ops.groupnorm(h, *r["gn1"], x1=skip, eps=1e-5, silu=True, want_raw="ws" in r)
         fv = film[:, r["film_off"]: r["film_off"] + r["cout"]]
-        _, h1 = ops.gemm(hn, r["w1"], taps=9, bias=r["b1"], film=fv, want_f32=True, splits=-1, want_stats=True)
+        _, h1 = ops.gemm(hn, r["w1"], taps=9, bias=r["b1"], film=fv, want_f32=True, splits=-1, want_stats=True, stats_group=self._sg)
         h1 = h1.view(nb, H, Wd, r["cout"])
         hn2, _ = ops.groupnorm(h1, *r["gn2"], eps=1e-5, silu=True)
         if x3:    # skip 1x1 conv on the raw stream: [x_hi | x_lo | x_hi] . [W_hi | W_hi | W_lo]
@@ -259,7 +269,7 @@ class UNetModel(nn.Module):
             assert skip is None
             res = h.view(-1, r["cout"])
         o16, out = ops.gemm(hn2, r["w2"], taps=9, bias=r["b2"], residual=res, want_f32=True, want_f16=emit_f16, splits=-1,
-                            want_stats=True)
+                            want_stats=True, stats_group=self._sg)
         out = out.view(nb, H, Wd, r["cout"])
         if emit_f16:
             out._sdb_f16 = o16.view(nb, H, Wd, r["cout"])
@@ -300,15 +310,16 @@ class UNetModel(nn.Module):
         _, t2 = ops.gemm(o.view(-1, ch), s["w_o2"], bias=s["b_o2"], residual=t1, want_f32=True, splits=-1)
         # --- GEGLU feed-forward
         y = ops.layernorm(t2, *s["ln3"])
-        g, _ = ops.gemm(y, s["w_ff1"], bias=s["b_ff1"], act=ACT_GEGLU, want_f16=True)
+        g, _ = ops.gemm(y, s["w_ff1"], bias=s["b_ff1"], act=ACT_GEGLU, want_f16=True,
+                        block_n=_geglu_tile(s["w_ff1"].shape[0] // 2))
         if x3:
             t3, _, t3_lo = ops.gemm(g, s["w_ff2"], bias=s["b_ff2"], residual=t2, want_lo=True, splits=-1)
             o16, out = ops.gemm(t3, s["w_out"], a1=t3_lo, a2=t3, bias=s["b_out"], residual=x.view(-1, ch), want_f32=True,
-                                want_f16=emit_f16, splits=-1, rows_per_sample=ntok, want_stats=True)
+                                want_f16=emit_f16, splits=-1, rows_per_sample=ntok, want_stats=True, stats_group=self._sg)
         else:
             t3, _ = ops.gemm(g, s["w_ff2"], bias=s["b_ff2"], residual=t2, want_f16=True, splits=-1)
             o16, out = ops.gemm(t3, s["w_out"], bias=s["b_out"], residual=x.view(-1, ch), want_f32=True,
-                                want_f16=emit_f16, splits=-1, rows_per_sample=ntok, want_stats=True)
+                                want_f16=emit_f16, splits=-1, rows_per_sample=ntok, want_stats=True, stats_group=self._sg)
         out = out.view(nb, H, Wd, ch)
         if emit_f16:
             out._sdb_f16 = o16.view(nb, H, Wd, ch)
@@ -371,17 +382,17 @@ class UNetModel(nn.Module):
                 h16 = getattr(h, "_sdb_f16", None)
                 if h16 is None:
                     h16 = ops.cast_f16(h)
-                _, o = ops.gemm(h16, p["w"], taps=9, conv_stride=2, bias=p["b"], want_f32=True, splits=-1, want_stats=True)
+                _, o = ops.gemm(h16, p["w"], taps=9, conv_stride=2, bias=p["b"], want_f32=True, splits=-1, want_stats=True, stats_group=self._sg)
                 h = o.view(nb, (H + 1) // 2, (Wd + 1) // 2, c)
             elif kind == "up":
                 nb, H, Wd, c = h.shape
                 up = ops.upsample2x(h)
-                _, o = ops.gemm(up, p["w"], taps=9, bias=p["b"], want_f32=True, splits=-1, want_stats=True)
+                _, o = ops.gemm(up, p["w"], taps=9, bias=p["b"], want_f32=True, splits=-1, want_stats=True, stats_group=self._sg)
                 h = o.view(nb, 2 * H, 2 * Wd, c)
             elif kind == "conv_in":
                 nb, H, Wd, c = h.shape
                 col = ops.im2col3x3(h, 1, 1, H, Wd, 64)
-                _, o = ops.gemm(col, p["w"], bias=p["b"], want_f32=True, rows_per_sample=H * Wd, want_stats=True)
+                _, o = ops.gemm(col, p["w"], bias=p["b"], want_f32=True, rows_per_sample=H * Wd, want_stats=True, stats_group=self._sg)
                 h = o.view(nb, H, Wd, p["cout"])
         return h
 

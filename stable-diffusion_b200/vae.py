@@ -17,6 +17,11 @@ from .unet import _pack_conv3, _pack_conv3_padk
 from .util import adopt_state_dict
 
 
+def _sg(c):
+    """Channels per fused-statistics entry for a c-channel tensor that feeds GroupNorm(32): one entry per group."""
+    return c // 32 if c % 32 == 0 and c >= 32 else 1
+
+
 class DiagonalGaussianDistribution:
     """distributions.py:24-62 on device tensors: parameters NCHW = [mean | logvar]."""
 
@@ -149,11 +154,13 @@ class AutoencoderKL(nn.Module):
         if c["col"]:
             nb, H, Wd, _ = x32.shape
             col = ops.im2col3x3(x32, 1, 1, H, Wd, c["w"].shape[1])
-            _, o = ops.gemm(col, c["w"], bias=c["b"], want_f32=True, rows_per_sample=H * Wd, want_stats=True, **epi)
+            _, o = ops.gemm(col, c["w"], bias=c["b"], want_f32=True, rows_per_sample=H * Wd, want_stats=True,
+                            stats_group=_sg(c["cout"]), **epi)
             return o.view(nb, H, Wd, c["cout"])
         nb, H, Wd, _ = x16.shape
-        # every conv output here feeds a GroupNorm next: let the epilogue accumulate its statistics
-        _, o = ops.gemm(x16, c["w"], taps=9, bias=c["b"], want_f32=True, splits=-1, want_stats=True, **epi)
+        # every conv output here feeds a GroupNorm next: let the epilogue store its statistics partials
+        _, o = ops.gemm(x16, c["w"], taps=9, bias=c["b"], want_f32=True, splits=-1, want_stats=True,
+                        stats_group=_sg(c["cout"]), **epi)
         return o.view(nb, H, Wd, c["cout"])
 
     def _resnet(self, r, x):
@@ -192,7 +199,7 @@ class AutoencoderKL(nn.Module):
                 raise NotImplementedError("VAE attention needs h*w % 8 == 0")
             ops.gemm(p, vt.contiguous(), out_f16=o[b], b_dynamic=True)
         _, out = ops.gemm(o.view(-1, c), a["w_o"], bias=a["b_o"], residual=x.view(-1, c), want_f32=True,
-                          rows_per_sample=n, want_stats=True)
+                          rows_per_sample=n, want_stats=True, stats_group=_sg(c))
         return out.view(nb, H, Wd, c)
 
     # ------------------------------------------------------------------ public API
@@ -228,11 +235,11 @@ class AutoencoderKL(nn.Module):
             for r in lvl["blocks"]:
                 h = self._resnet(r, h)
             if lvl["resample"] is not None:   # Downsample: pad (0,1,0,1) + conv stride 2 pad 0 (model.py:60-79)
+                # straight from the NHWC activation through strided TMA boxes (conv_shift 1 = pad right / bottom only)
                 nb, H, Wd, c = h.shape
-                col = ops.im2col3x3(h, 2, 0, H // 2, Wd // 2, 9 * c)
                 rs = lvl["resample"]
-                _, o = ops.gemm(col, rs["w"], bias=rs["b"], want_f32=True, splits=-1,
-                                rows_per_sample=(H // 2) * (Wd // 2), want_stats=True)
+                _, o = ops.gemm(ops.cast_f16(h), rs["w"], taps=9, conv_stride=2, conv_shift=1, bias=rs["b"], want_f32=True,
+                                splits=-1, want_stats=True, stats_group=_sg(c))
                 h = o.view(nb, H // 2, Wd // 2, c)
         h = self._resnet(E["mid1"], h)
         h = self._attn(E["attn"], h)

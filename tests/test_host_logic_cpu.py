@@ -48,11 +48,16 @@ def test_pack_layouts():
     wq = torch.randn(2 * 40, 16, generator=g)
     ph = U._pack_heads(wq, 2, 40, 64)
     assert ph.shape == (128, 16) and float(ph[40:64].abs().max()) == 0 and torch.equal(ph[64:104], wq[40:].half())
-    # GEGLU packing: each 128-row tile = [64 value rows | 64 gate rows]
+    # GEGLU packing: each accumulator tile = [half value rows | half gate rows]; 256-wide tiles when the inner width
+    # is a multiple of 128 (inner 128 -> one tile [128 value | 128 gate]), else 128-wide (inner 192 -> 3 x [64 | 64])
     w2 = torch.arange(2 * 128 * 3, dtype=torch.float32).reshape(256, 3)
     b2 = torch.arange(256, dtype=torch.float32)
     pw, pb = U._pack_geglu(w2, b2)
-    assert torch.equal(pb[:64], b2[:64]) and torch.equal(pb[64:128], b2[128:192]) and torch.equal(pb[128:192], b2[64:128])
+    assert U._geglu_tile(128) == 256 and torch.equal(pb, b2) and torch.equal(pw, w2.half())
+    b3 = torch.arange(384, dtype=torch.float32)
+    _, pb3 = U._pack_geglu(torch.zeros(384, 3), b3)
+    assert U._geglu_tile(192) == 128
+    assert torch.equal(pb3[:64], b3[:64]) and torch.equal(pb3[64:128], b3[192:256]) and torch.equal(pb3[128:192], b3[64:128])
     # hi/lo split reproduces fp32 weights to ~2^-22
     w3 = torch.randn(32, 64, generator=g)
     p3 = U._pack_hilo_1x1(w3)

@@ -103,6 +103,117 @@ def test_conv3x3_concat_and_skip(S, cuda_dev):
     assert rel_l2(s32, ref2) < 1e-5
 
 
+def _check_stats(o32, nb, rps, n):
+    """Per-tile statistics partials attached by gemm(want_stats=True): summed over the tile slots they must equal the
+    per-(sample, channel group) sum / sum of squares of the fp32 output."""
+    st, T, sg = o32._sdb_stats
+    assert st.shape == (nb, T, n // sg, 2) and st.dtype == torch.float32
+    got = st.double().sum(1)
+    x = o32.double().view(nb, rps, n // sg, sg)
+    ref = torch.stack([x.sum((1, 3)), (x * x).sum((1, 3))], -1)
+    assert rel_l2(got, ref) < 1e-5, rel_l2(got, ref)
+
+
+@pytest.mark.parametrize("M,N,K,bn,sg", [
+    (8192, 320, 320, 160, 10), (2048, 640, 1280, 160, 10), (512, 1280, 640, 160, 10), (1000, 256, 192, 128, 4),
+    (256, 512, 128, 256, 1), (4096, 320, 960, 160, 10), (384, 320, 64, 160, 2),
+])
+def test_gemm_cta_pair(S, cuda_dev, M, N, K, bn, sg):
+    """cta_group::2: two CTAs per 256 x block_n tile, each loading half of the weight tile (odd tile counts included)."""
+    g = torch.Generator().manual_seed(M + N + K)
+    a = _rand16((M, K), cuda_dev, g)
+    b = _rand16((N, K), cuda_dev, g, K ** -0.5)
+    bias = torch.randn(N, generator=g).to(cuda_dev)
+    res = torch.randn(M, N, generator=g).to(cuda_dev)
+    rps = M if M % 128 == 0 else 0
+    o16, o32 = S.ops.gemm(a, b, bias=bias, residual=res, want_f16=True, want_f32=True, block_n=bn, pair=2,
+                          rows_per_sample=rps, want_stats=bool(rps), stats_group=sg)
+    torch.cuda.synchronize()
+    ref = a.double() @ b.double().t() + bias + res
+    assert rel_l2(o32, ref) < 1e-5, rel_l2(o32, ref)
+    assert rel_l2(o16.float(), ref) < 6e-4
+    if rps:
+        _check_stats(o32, 1, rps, N)
+
+
+@pytest.mark.parametrize("nb,h,w,c,n,bn,pair,sp", [
+    (2, 64, 64, 320, 320, 160, 2, 1), (2, 32, 32, 640, 640, 160, 2, 2), (2, 16, 16, 1280, 1280, 160, 2, 4),
+    (2, 8, 8, 1280, 1280, 160, 1, 4), (2, 16, 16, 640, 1280, 128, 1, 2), (3, 32, 32, 64, 256, 256, 2, 2),
+    (2, 8, 8, 320, 640, 160, 1, 2), (1, 16, 16, 128, 64, 64, 1, 4),
+])
+def test_conv3x3_pair_and_cluster_splitk(S, cuda_dev, nb, h, w, c, n, bn, pair, sp):
+    """3x3 convs on CTA pairs and with split-K reduced inside the cluster through distributed shared memory: fused
+    epilogue (bias, FiLM, residual, fp16 + fp32 outputs) and the per-tile statistics partials."""
+    g = torch.Generator().manual_seed(nb * 131 + h + c + sp)
+    x = _rand16((nb, h, w, c), cuda_dev, g)
+    wt = _rand16((n, c, 3, 3), cuda_dev, g, (9 * c) ** -0.5)
+    bias = torch.randn(n, generator=g).to(cuda_dev)
+    film = torch.randn(nb, n, generator=g).to(cuda_dev)
+    res = torch.randn(nb * h * w, n, generator=g).to(cuda_dev)
+    wk = wt.permute(0, 2, 3, 1).reshape(n, 9 * c).contiguous()
+    sg = 10 if n % 10 == 0 and bn % 10 == 0 else 2
+    o16, o32 = S.ops.gemm(x, wk, taps=9, bias=bias, film=film, residual=res, want_f32=True, want_f16=True, block_n=bn,
+                          pair=pair, splits=sp, splitk_mode=2 if sp > 1 else 0, want_stats=True, stats_group=sg)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.double().permute(0, 3, 1, 2), wt.double(), bias.double(), padding=1) + film[:, :, None, None]
+    ref = ref.permute(0, 2, 3, 1).reshape(nb * h * w, n) + res
+    assert rel_l2(o32, ref) < 1e-5, rel_l2(o32, ref)
+    assert rel_l2(o16.float(), ref) < 6e-4
+    _check_stats(o32, nb, h * w, n)
+    # bit-reproducible: fixed-order reduction, no atomics anywhere
+    o16b, o32b = S.ops.gemm(x, wk, taps=9, bias=bias, film=film, residual=res, want_f32=True, want_f16=True, block_n=bn,
+                            pair=pair, splits=sp, splitk_mode=2 if sp > 1 else 0, want_stats=True, stats_group=sg)
+    assert torch.equal(o32, o32b) and torch.equal(o32._sdb_stats[0], o32b._sdb_stats[0])
+
+
+@pytest.mark.parametrize("M,N,K,sp,pair", [(128, 1280, 5120, 4, 1), (512, 1280, 5120, 4, 2), (2048, 640, 2560, 2, 2),
+                                            (512, 320, 1280, 2, 1), (640, 1280, 1920, 2, 2)])
+def test_gemm_cluster_splitk_plain(S, cuda_dev, M, N, K, sp, pair):
+    g = torch.Generator().manual_seed(M + K + sp)
+    a = _rand16((M, K), cuda_dev, g)
+    b = _rand16((N, K), cuda_dev, g, K ** -0.5)
+    bias = torch.randn(N, generator=g).to(cuda_dev)
+    res = torch.randn(M, N, generator=g).to(cuda_dev)
+    o16, o32, lo = S.ops.gemm(a, b, bias=bias, residual=res, want_f32=True, want_lo=True, block_n=160 if N % 160 == 0 else 128,
+                              pair=pair, splits=sp, splitk_mode=2)
+    ref = a.double() @ b.double().t() + bias + res
+    assert rel_l2(o32, ref) < 1e-5, rel_l2(o32, ref)
+    assert rel_l2(o16.float() + lo.float(), ref) < 2e-6
+
+
+def test_gemm_workspace_splitk_statistics(S, cuda_dev):
+    """Workspace split-K (second kernel) also writes the per-block statistics partials."""
+    g = torch.Generator().manual_seed(21)
+    nb, h, w, c, n = 2, 8, 8, 640, 1280
+    x = _rand16((nb, h, w, c), cuda_dev, g)
+    wk = _rand16((n, 9 * c), cuda_dev, g, (9 * c) ** -0.5)
+    _, o32 = S.ops.gemm(x, wk, taps=9, want_f32=True, splits=6, splitk_mode=1, want_stats=True, stats_group=10)
+    wt = wk.reshape(n, 3, 3, c).permute(0, 3, 1, 2).double()
+    ref = F.conv2d(x.double().permute(0, 3, 1, 2), wt, padding=1).permute(0, 2, 3, 1).reshape(-1, n)
+    assert rel_l2(o32, ref) < 1e-5
+    _check_stats(o32, nb, h * w, n)
+
+
+def test_gemm_geglu_wide_tile_on_cta_pairs(S, cuda_dev):
+    """GEGLU with 256-wide accumulator tiles ([128 value | 128 gate]) on CTA pairs and on single CTAs."""
+    g = torch.Generator().manual_seed(12)
+    K, inner = 320, 1280
+    wfull = _rand16((2 * inner, K), cuda_dev, g, K ** -0.5)
+    bfull = torch.randn(2 * inner, generator=g).to(cuda_dev)
+    idx = []
+    for t in range(inner // 128):
+        idx += list(range(t * 128, t * 128 + 128)) + list(range(inner + t * 128, inner + t * 128 + 128))
+    idx = torch.tensor(idx, device=cuda_dev)
+    wp, bp = wfull[idx].contiguous(), bfull[idx].contiguous()
+    for M, pair in ((1000, 2), (128, 1), (8192, 2)):
+        a = _rand16((M, K), cuda_dev, g)
+        o16, _ = S.ops.gemm(a, wp, bias=bp, act=S.ops.ACT_GEGLU, want_f16=True, block_n=256, pair=pair)
+        y = a.float() @ wfull.float().t() + bfull
+        ref = y[:, :inner] * F.gelu(y[:, inner:])
+        assert o16.shape == (M, inner)
+        assert rel_l2(o16.float(), ref) < 8e-4, (M, pair, rel_l2(o16.float(), ref))
+
+
 @pytest.mark.parametrize("splits", [2, 5, 9])
 def test_gemm_splitk(S, cuda_dev, splits):
     g = torch.Generator().manual_seed(splits)
@@ -302,23 +413,22 @@ def test_gemm_narrow_tiles_many_per_cta(S, cuda_dev):
 
 
 def test_gemm_fused_groupnorm_stats_and_inkernel_splitk(S, cuda_dev):
-    """Epilogue-accumulated per-channel statistics feed groupnorm() without a reduction pass; split-K partials are
-    reduced by the last-arriving CTA inside the GEMM kernel."""
+    """Per-tile statistics partials stored by the GEMM epilogue (any split-K mode, entries of 1 / 2 / 10 channels) feed
+    groupnorm() without a reduction pass, also across a channel concat and through the large-image fold kernel."""
     g = torch.Generator().manual_seed(31)
-    for (nb, h, w, c, n, splits) in [(2, 16, 16, 128, 320, 0), (2, 8, 8, 320, 640, 4), (3, 8, 8, 64, 64, -1), (2, 32, 32, 64, 128, 0)]:
+    for (nb, h, w, c, n, splits, sg) in [(2, 16, 16, 128, 320, 0, 10), (2, 8, 8, 320, 640, 4, 10), (3, 8, 8, 64, 64, -1, 2),
+                                         (2, 32, 32, 64, 128, 0, 1), (1, 128, 128, 64, 128, 0, 4), (2, 24, 24, 64, 320, 0, 10), (3, 24, 24, 128, 160, 2, 10)]:
         x = _rand16((nb, h, w, c), cuda_dev, g)
         wk = _rand16((n, 9 * c), cuda_dev, g, (9 * c) ** -0.5)
         bias = torch.randn(n, generator=g).to(cuda_dev)
         res = (torch.randn(nb * h * w, n, generator=g) * 2 + 0.7).to(cuda_dev)
-        _, o32 = S.ops.gemm(x, wk, taps=9, bias=bias, residual=res, want_f32=True, splits=splits, want_stats=True)
+        _, o32 = S.ops.gemm(x, wk, taps=9, bias=bias, residual=res, want_f32=True, splits=splits, want_stats=True,
+                            stats_group=sg)
         wt = wk.reshape(n, 3, 3, c).permute(0, 3, 1, 2).double()
         ref = F.conv2d(x.double().permute(0, 3, 1, 2), wt, bias.double(), padding=1).permute(0, 2, 3, 1).reshape(-1, n) + res
         assert rel_l2(o32, ref) < 1e-5, (nb, h, w, c, n, splits, rel_l2(o32, ref))
-        st = S.ops.channel_stats(o32)
-        assert st is not None and st.shape == (4, nb, n, 2)
-        st = st.sum(0)
-        r3 = ref.reshape(nb, h * w, n)
-        assert rel_l2(st[..., 0], r3.sum(1)) < 1e-5 and rel_l2(st[..., 1], (r3 * r3).sum(1)) < 1e-5
+        assert S.ops.channel_stats(o32) is not None
+        _check_stats(o32, nb, h * w, n)
         gamma = (1 + 0.1 * torch.randn(n, generator=g)).to(cuda_dev)
         beta = (0.1 * torch.randn(n, generator=g)).to(cuda_dev)
         y, _ = S.ops.groupnorm(o32.view(nb, h, w, n), gamma, beta, eps=1e-5, silu=True)   # uses the fused stats
@@ -328,8 +438,8 @@ def test_gemm_fused_groupnorm_stats_and_inkernel_splitk(S, cuda_dev):
     xa = _rand16((2, 8, 8, 64), cuda_dev, g)
     wa = _rand16((192, 9 * 64), cuda_dev, g, 0.05)
     wb = _rand16((64, 9 * 64), cuda_dev, g, 0.05)
-    _, a32 = S.ops.gemm(xa, wa, taps=9, want_f32=True, want_stats=True)
-    _, b32 = S.ops.gemm(xa, wb, taps=9, want_f32=True, want_stats=True)
+    _, a32 = S.ops.gemm(xa, wa, taps=9, want_f32=True, want_stats=True, stats_group=2)
+    _, b32 = S.ops.gemm(xa, wb, taps=9, want_f32=True, want_stats=True, stats_group=2, splits=2, splitk_mode=2)
     gam = torch.ones(256, device=cuda_dev)
     bet = torch.zeros(256, device=cuda_dev)
     y, _ = S.ops.groupnorm(a32.view(2, 8, 8, 192), gam, bet, x1=b32.view(2, 8, 8, 64), eps=1e-6)
