@@ -12,6 +12,8 @@
 #include "host.h"
 #include "ptx.cuh"
 
+#include <stdlib.h>
+
 namespace sdb {
 
 constexpr int AQ = 128;   // query rows per CTA
@@ -282,6 +284,275 @@ __global__ void __launch_bounds__(192)
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Split-state variant for DPAD == 64, d < 64 (the 64x64-latent self-attention of SD v1: N = 4096, d = 40 - 13 % of a
+// UNet evaluation with the kernel above, which keeps one softmax thread per query row: 2 softmax warps per scheduler,
+// MUFU pipe 42 % busy, the row maximum / exponent / pack phases of a warp strictly serial).
+//
+//   * every query row is handled by TWO threads, each owning 32 of the 64 key columns of a KV tile and its OWN online-
+//     softmax state (running maximum) and its own output accumulator: O_A += P[:, 0:32] V[0:32], O_B += P[:, 32:64] V[32:64]
+//     (the same four K = 16 MMAs, two per accumulator). The two halves never talk inside the loop; they are merged once
+//     at the end: O = (2^(mA-m) O_A + 2^(mB-m) O_B) / (2^(mA-m) lA + 2^(mB-m) lB). Eight softmax warps per CTA, four per
+//     scheduler with two co-resident CTAs, ~70 registers per thread.
+//   * the row sums come out of the tensor cores: row d of every V^T tile in shared memory is a constant row of ones
+//     (TMA only writes rows 0 .. d-1 of the tile; rows d .. 63 are initialised once), so column d of each accumulator
+//     is sum_j P[i, j] - consistent with the fp16-rounded P the numerator uses, rescaled together with O, no FADD chain.
+//   * the block maximum uses 3-input FMNMX.
+constexpr int SPLIT_THREADS = 64 + 256;
+constexpr int SPLIT_ST = 3;
+constexpr int SPLIT_SMEM = AQ * 64 * 2 + SPLIT_ST * (2 * AKV * 64 * 2) + 2 * AQ * AKV * 2 + 1024;
+
+__global__ void __launch_bounds__(SPLIT_THREADS, 2)
+    attention_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                           const __grid_constant__ CUtensorMap tmV, const AttnArgs p) {
+  constexpr int DPAD = 64;
+  constexpr int Q_BYTES = AQ * DPAD * 2;
+  constexpr int K_BYTES = AKV * DPAD * 2;
+  constexpr int V_BYTES = DPAD * AKV * 2;
+  constexpr int P_BYTES = AQ * AKV * 2;
+  constexpr int TMEM_COLS = 256;
+  constexpr int ST = SPLIT_ST;
+  constexpr uint32_t O_COL = 128;   // O_A at 128, O_B at 192
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* q_s = smem;
+  uint8_t* k_s = q_s + Q_BYTES;
+  uint8_t* v_s = k_s + ST * K_BYTES;
+  uint8_t* p_s = v_s + ST * V_BYTES;
+
+  __shared__ uint64_t q_full, k_full[ST], v_full[ST], kv_empty[ST], s_full[2], p_full[2], pv_done[2];
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ float m_sh[2][AQ];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  const int q0 = blockIdx.x * AQ;
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  int nkv_eff = p.nkv;
+  if (p.causal) nkv_eff = min(p.nkv, q0 + AQ);
+  const int n_iter = (nkv_eff + AKV - 1) / AKV;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(&q_full, 1);
+    for (int i = 0; i < ST; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 256);
+      mbar_init(&pv_done[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_smem, TMEM_COLS);
+    tmem_relinquish();
+  }
+  {
+    // constant rows of the V^T tiles: row d = ones, rows d+1 .. 63 = zeros (16-byte granules; a constant row is
+    // invariant under the 128-byte swizzle). TMA never writes them.
+    const int granules = (DPAD - p.d) * 8;
+    for (int i = threadIdx.x; i < ST * granules; i += SPLIT_THREADS) {
+      const int st = i / granules, g = i - st * granules;
+      const uint32_t val = (g < 8) ? 0x3C003C00u : 0u;
+      *reinterpret_cast<uint4*>(v_s + st * V_BYTES + p.d * 128 + g * 16) = make_uint4(val, val, val, val);
+    }
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_smem;
+
+  pdl_wait();
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint32_t v_load_bytes = static_cast<uint32_t>(p.d) * AKV * 2;
+      mbar_arrive_expect_tx(&q_full, Q_BYTES);
+      tma_load_3d(q_s, &tmQ, &q_full, head * DPAD, q0, b);
+      for (int j = 0; j < n_iter; ++j) {
+        int s = j % ST;
+        uint32_t ph = (j / ST) & 1;
+        mbar_wait(&kv_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&k_full[s], K_BYTES);
+        tma_load_3d(k_s + s * K_BYTES, &tmK, &k_full[s], head * DPAD, j * AKV, b);
+        mbar_arrive_expect_tx(&v_full[s], v_load_bytes);
+        tma_load_3d(v_s + s * V_BYTES, &tmV, &v_full[s], j * AKV, head * DPAD, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc_s = umma_idesc_f16(AQ, AKV);
+      constexpr uint32_t idesc_o = umma_idesc_f16(AQ, DPAD);
+      const uint32_t q_addr = smem_u32(q_s);
+      auto issue_s = [&](int j) {
+        const int s = j & 1;
+        const int ks = j % ST;
+        mbar_wait(&k_full[ks], (j / ST) & 1);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(k_s + ks * K_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < DPAD / 16; ++kk) {
+          uint64_t da = umma_desc_k128(q_addr + kk * 32);
+          uint64_t db = umma_desc_k128(k_addr + kk * 32);
+          umma_f16(tmem + s * AKV, da, db, idesc_s, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[s]);
+      };
+      mbar_wait(&q_full, 0);
+      if (n_iter > 0) issue_s(0);
+      for (int j = 0; j < n_iter; ++j) {
+        int s = j & 1;
+        uint32_t ph = (j >> 1) & 1;
+        if (j + 1 < n_iter) issue_s(j + 1);
+        const int ks = j % ST;
+        mbar_wait(&p_full[s], ph);
+        mbar_wait(&v_full[ks], (j / ST) & 1);
+        tc_fence_after();
+        const uint32_t p_addr = smem_u32(p_s + s * P_BYTES);
+        const uint32_t v_addr = smem_u32(v_s + ks * V_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < AKV / 16; ++kk) {   // key columns 0-31 -> O_A, 32-63 -> O_B
+          uint64_t da = umma_desc_k128(p_addr + kk * 32);
+          uint64_t db = umma_desc_k128(v_addr + kk * 32);
+          umma_f16(tmem + O_COL + (kk >> 1) * DPAD, da, db, idesc_o, (j > 0 || (kk & 1)) ? 1u : 0u);
+        }
+        umma_commit(&kv_empty[ks]);
+        umma_commit(&pv_done[s]);
+      }
+    }
+  } else {
+    const int lg = warp & 3;
+    const int hf = (warp - 2) >> 2;   // key-column half of every KV tile this thread owns
+    const int r = lg * 32 + lane;
+    const int qi = q0 + r;
+    const uint32_t lane_addr = static_cast<uint32_t>(lg * 32) << 16;
+    const uint32_t o_addr = tmem + lane_addr + O_COL + hf * DPAD;
+    float m_used = -INFINITY;
+    for (int j = 0; j < n_iter; ++j) {
+      const int s = j & 1;
+      mbar_wait(&s_full[s], (j >> 1) & 1);
+      tc_fence_after();
+      float t[32];
+      {
+        uint32_t r0[32];
+        tmem_ld32(tmem + lane_addr + s * AKV + hf * 32, r0);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) t[c] = __uint_as_float(r0[c]);
+      }
+      const int kv0 = j * AKV + hf * 32;
+      if ((kv0 + 32 > p.nkv) || (p.causal && kv0 + 31 > q0)) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          int kv = kv0 + c;
+          if ((kv >= p.nkv) || (p.causal && kv > qi)) t[c] = -INFINITY;
+        }
+      }
+      float mx[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) mx[i] = fmaxf(fmaxf(t[i], t[4 + i]), t[8 + i]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) mx[i] = fmaxf(fmaxf(mx[i], t[12 + i]), t[16 + i]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) mx[i] = fmaxf(fmaxf(mx[i], t[20 + i]), t[24 + i]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) mx[i] = fmaxf(mx[i], t[28 + i]);
+      const float m_blk = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * p.scale_log2;  // scale > 0
+      {
+        const float m_new = fmaxf(m_used, m_blk);
+        const bool need = m_new > m_used + 8.0f;   // also true for the first finite block (m_used = -inf)
+        if (j > 0 && __any_sync(0xffffffffu, need)) {
+          mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);   // O may only be touched once PV(j-1) has landed
+          tc_fence_after();
+          const float alpha = need ? exp2f(m_used - m_new) : 1.0f;   // exp2f(-inf) = 0: nothing accumulated yet
+#pragma unroll 1
+          for (int c = 0; c < DPAD / 32; ++c) {
+            uint32_t o[32];
+            tmem_ld32(o_addr + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(o_addr + c * 32, o);
+          }
+          tmem_st_wait();
+        }
+        if (need) m_used = m_new;
+      }
+      const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used;   // a fully masked half so far: exp2(-inf) = 0
+#pragma unroll
+      for (int c = 0; c < 32; ++c) t[c] = fast_exp2(fmaf(t[c], p.scale_log2, neg_m));
+      if (j >= 2) mbar_wait(&pv_done[s], ((j - 2) >> 1) & 1);  // P buffer s was read by PV(j-2)
+      uint8_t* prow = p_s + s * P_BYTES + r * 128;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        __half2 h0 = __floats2half2_rn(t[i * 8 + 0], t[i * 8 + 1]);
+        __half2 h1 = __floats2half2_rn(t[i * 8 + 2], t[i * 8 + 3]);
+        __half2 h2 = __floats2half2_rn(t[i * 8 + 4], t[i * 8 + 5]);
+        __half2 h3 = __floats2half2_rn(t[i * 8 + 6], t[i * 8 + 7]);
+        uint4 u;
+        u.x = *reinterpret_cast<uint32_t*>(&h0);
+        u.y = *reinterpret_cast<uint32_t*>(&h1);
+        u.z = *reinterpret_cast<uint32_t*>(&h2);
+        u.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(prow + (((hf * 4 + i) ^ (r & 7)) << 4)) = u;
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(&p_full[s]);
+    }
+    // merge the two halves: O = (fA O_A + fB O_B) / (fA lA + fB lB), l = column d of each accumulator
+    m_sh[hf][r] = m_used;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (n_iter > 0) {
+      mbar_wait(&pv_done[(n_iter - 1) & 1], ((n_iter - 1) >> 1) & 1);
+      tc_fence_after();
+    }
+    const float mA = m_sh[0][r], mB = m_sh[1][r];
+    const float m = fmaxf(mA, mB);
+    const float fA = (mA == -INFINITY) ? 0.f : exp2f(mA - m);
+    const float fB = (mB == -INFINITY) ? 0.f : exp2f(mB - m);
+    const uint32_t oa = tmem + lane_addr + O_COL, ob = oa + DPAD;
+    float inv_l = 0.f;
+    uint32_t a[32], bb[32];
+    if (n_iter > 0) {
+      const uint32_t la = tmem_ld1(oa + p.d), lb = tmem_ld1(ob + p.d);
+      tmem_ld32(oa + hf * 32, a);
+      tmem_ld32(ob + hf * 32, bb);
+      tmem_ld_wait();
+      const float l = fA * __uint_as_float(la) + fB * __uint_as_float(lb);
+      inv_l = l > 0.f ? 1.0f / l : 0.f;
+    }
+    if (qi < p.nq && n_iter > 0) {
+      __half* orow = p.out + static_cast<size_t>(b) * p.o_batch_stride + static_cast<size_t>(qi) * p.ldo + head * p.d;
+      const float ga = fA * inv_l, gb = fB * inv_l;
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        const int col = hf * 32 + i;
+        if (col < p.d)
+          *reinterpret_cast<__half2*>(orow + col) =
+              __floats2half2_rn(__uint_as_float(a[i]) * ga + __uint_as_float(bb[i]) * gb,
+                                __uint_as_float(a[i + 1]) * ga + __uint_as_float(bb[i + 1]) * gb);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, TMEM_COLS);
+  }
+}
+
 template <int DPAD>
 static int launch_attn(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnArgs& p, dim3 grid,
                        cudaStream_t st) {
@@ -325,10 +596,17 @@ extern "C" int sdb_attention(const sdb_attn_desc* d, sdb_stream_t stream) {
     uint32_t box[3] = {64, AKV, 1};
     if (make_tmap_f16(&tk, d->k, 3, dims, str, box)) return 1;
   }
+  // split-state kernel (two threads per query row, row sums from a ones row of V^T): dpad 64 with spare rows
+  static int split_off = -1;
+  if (split_off < 0) {
+    const char* e = getenv("SDB_ATTN_SPLIT");
+    split_off = (e && e[0] == '0') ? 1 : 0;
+  }
+  const bool use_split = d->dpad == 64 && d->d < 64 && d->d % 8 == 0 && !split_off;
   {
     uint64_t dims[3] = {static_cast<uint64_t>(d->nkv), hd, static_cast<uint64_t>(d->batch)};
     uint64_t str[2] = {static_cast<uint64_t>(d->ldvt) * 2, static_cast<uint64_t>(d->vt_batch_stride) * 2};
-    uint32_t box[3] = {AKV, static_cast<uint32_t>(d->dpad), 1};
+    uint32_t box[3] = {AKV, static_cast<uint32_t>(use_split ? d->d : d->dpad), 1};   // split: only the d real rows
     if (make_tmap_f16(&tv, d->vt, 3, dims, str, box)) return 1;
   }
   AttnArgs p{};
@@ -342,6 +620,16 @@ extern "C" int sdb_attention(const sdb_attn_desc* d, sdb_stream_t stream) {
   p.scale_log2 = d->scale * 1.4426950408889634f;
   p.causal = d->causal;
   dim3 grid((d->nq + AQ - 1) / AQ, d->heads, d->batch);
+  if (use_split) {
+    static bool configured = false;
+    if (!configured) {
+      SDB_CUDA(cudaFuncSetAttribute(attention_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SPLIT_SMEM));
+      configured = true;
+    }
+    SDB_CUDA(launch_pdl(attention_split_kernel, grid, dim3(SPLIT_THREADS), SPLIT_SMEM, st, tq, tk, tv, p));
+    SDB_LAUNCH_CHECK();
+    return 0;
+  }
   switch (d->dpad) {
     case 64: return launch_attn<64>(tq, tk, tv, p, grid, st);
     case 128: return launch_attn<128>(tq, tk, tv, p, grid, st);

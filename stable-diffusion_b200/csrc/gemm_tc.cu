@@ -48,6 +48,9 @@ constexpr int STG_WARP_BYTES = 8192;  // per epilogue warp: 2 x 4 KB fp32 tiles,
 constexpr int STAGING_BYTES = EPI_WARPS * STG_WARP_BYTES;
 constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS + 32;   // + warp 10: weight (B) tile producer
 constexpr int B_WARP = 2 + EPI_WARPS;
+// single-tile (DEEP) epilogue: every epilogue warp stages ALL its chunks (<= 4) in a private 24 KB slice of the idle
+// operand ring: 4 x 4 KB fp32 tiles + 4 x 2 KB fp16 tiles (or 4 x (2 KB hi + 2 KB lo) when there is no fp32 output)
+constexpr int DEEP_WARP_STG = 24576;
 
 struct TmapPack {
   CUtensorMap a[MAX_SRC];
@@ -56,6 +59,7 @@ struct TmapPack {
   CUtensorMap o16;   // fp16 output, same geometry, SWIZZLE_64B
   CUtensorMap o16lo; // fp16 low half
   CUtensorMap ows;   // split-K fp32 partial planes [C, W, H, NB, splits]
+  CUtensorMap res;   // fp32 residual, geometry of o32 (loaded into the staging tiles by the single-tile epilogue)
 };
 
 struct GemmArgs {
@@ -89,6 +93,7 @@ struct GemmArgs {
   int n_samples;
   int b_static;     // B is a weight matrix: safe to prefetch before griddepcontrol.wait
   int fast;         // outputs go through the TMA-store epilogue
+  int res_tma;      // the residual has a tensor map (tm.res): the single-tile epilogue loads it by TMA
   int bw, bh;       // store box: bw x bh x (32 / (bw*bh)) output pixels per epilogue warp
   int cstride, cshift;   // 3x3 conv: input pixel = cstride * o + tap - 1 + cshift (per axis)
   int film_table;   // 1: rows 0-63 / 64-127 of every tile belong to one sample each, so bias + FiLM fold into a
@@ -248,6 +253,7 @@ struct GemmCfg {
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
   static constexpr int SMEM = RING_BYTES + (DEEP ? 0 : STAGING_BYTES) + 1024;
   static_assert(!DEEP || RING_BYTES >= BN * 512 + STAGING_BYTES, "cluster split-K receive area + staging must fit the ring");
+  static_assert(!DEEP || RING_BYTES >= EPI_WARPS * DEEP_WARP_STG, "whole-tile staging must fit the ring");
 };
 
 struct EpiRows {   // the output rows one epilogue warp handles: row per lane + the TMA store box origin
@@ -272,6 +278,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   __shared__ uint64_t empty_bar[STAGES];
   __shared__ uint64_t acc_full[2];
   __shared__ uint64_t acc_empty[2];
+  __shared__ uint64_t res_bar[EPI_WARPS];   // single-tile epilogue: residual tiles of one warp have landed
   __shared__ uint32_t tmem_base_smem;
   // fused GroupNorm statistics: [lane group][column][sum, sum of squares]; one writer per slot per tile, fixed-order
   // fold at the flush, plain stores of the per-tile partials (deterministic)
@@ -323,6 +330,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       if (p.out_f32) tma_prefetch_desc(&tm.o32);
       if (p.out_f16) tma_prefetch_desc(&tm.o16);
       if (p.out_f16_lo) tma_prefetch_desc(&tm.o16lo);
+      if (p.res_tma) tma_prefetch_desc(&tm.res);
     }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);      // CTA pair: armed by the leader alone, with the bytes of BOTH CTAs
@@ -332,6 +340,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], EPI_WARPS * CG);
     }
+    for (int i = 0; i < EPI_WARPS; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -351,7 +360,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = tmem_base_smem;
-  if (threadIdx.x == 0) SDB_TR(2, clock64() - clk0);
+  if (threadIdx.x == 0 && !(p.dbg & 64)) SDB_TR(2, clock64() - clk0);
 
   // ---------------------------------------------------------------- epilogue state and helpers (warps 2..9)
   const int ew = (warp - 2) & 7;
@@ -371,6 +380,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   const bool use_tab = p.fast && !split_fast;
   const bool pre_res = use_tab && !geglu && p.residual != nullptr;
   uint32_t flip = 0;
+  bool tr_chunk = false;   // debug (SDB_DBG bit 6): sub-phase stamps of the first chunk of epilogue warp 0
 
   auto rows_of = [&](int m_tile, int lgx) {
     EpiRows rw;
@@ -461,6 +471,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
       }
     }
+    if (tr_chunk) SDB_TR(4, clock64() - clk0);
     const bool w32 = raw_partial || p.out_f32;
     const bool w16 = !raw_partial && p.out_f16;
     const bool w16lo = w16 && p.out_f16_lo;
@@ -510,6 +521,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     }
     fence_proxy_async();
     __syncwarp();
+    if (tr_chunk) SDB_TR(5, clock64() - clk0);
     if (lane == 0 && !(p.dbg & 4)) {
       if (raw_partial) {
         tma_store_5d(&tm.ows, s32, ocol0, rw.sx, rw.sy, rw.sn, split);
@@ -560,6 +572,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           *reinterpret_cast<float2*>(&colsum[(lgx * BN + cl + j) * 2]) = make_float2(cs[j], cq[j]);
       }
     }
+    if (tr_chunk) SDB_TR(2, clock64() - clk0);
     ++flip;
   };
   // per-tile flush of the fused GroupNorm column sums: one {sum, sum of squares} entry per group of stats_sg
@@ -616,7 +629,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       const uint32_t arm_bytes = (((p.dbg & 8) ? 0u : Cfg::B_BYTES) + ((p.dbg & 32) ? 0u : A_BYTES)) * CG;
       const uint32_t smem_base = smem_u32(smem) + (is_a ? 0u : static_cast<uint32_t>(A_BYTES));
       if (is_a || !p.b_static) pdl_wait();
-      if (is_a) SDB_TR(3, clock64() - clk0);
+      if (is_a && !(p.dbg & 64)) SDB_TR(3, clock64() - clk0);
       int s = 0;
       uint32_t ph = 0;
       bool ring_pass = false;
@@ -721,7 +734,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           if (first_data) {
-            SDB_TR(4, clock64() - clk0);
+            if (!(p.dbg & 64)) SDB_TR(4, clock64() - clk0);
             first_data = false;
           }
           if (!(p.dbg & 16)) {
@@ -745,7 +758,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         if (CG == 2) umma_commit_cg2(&acc_full[ab], cmask);
         else umma_commit(&acc_full[ab]);
       }
-      SDB_TR(5, clock64() - clk0);
+      if (!(p.dbg & 64)) SDB_TR(5, clock64() - clk0);
     }
     __syncwarp();
   } else if (!p.csk && warp < B_WARP) {
@@ -765,8 +778,225 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         else mbar_arrive(&acc_empty[ab]);
       }
     };
+    bool whole_tile_done = false;
+    if constexpr (DEEP) {
+      if (p.fast && !geglu && !(st32 && st16 && p.out_f16_lo)) {
+        // ---- single-tile epilogue. The CTA owns exactly one tile and the operand ring is idle once the accumulator is
+        // complete, so every warp stages ALL its chunks in a private slice of it: the TMEM loads of two chunks are in
+        // flight together, the residual tile arrives by TMA (in the swizzled layout of the store boxes - a row-per-thread
+        // global read costs 32 L1 wavefronts per instruction) straight into the fp32 staging tile and is summed in place,
+        // nothing waits for a staging buffer to be recycled, and there is one proxy fence + one bulk group per batch.
+        // (Plain 16-byte global stores from a second row-contiguous pass were measured 30-90 % slower than the bulk
+        // stores: the epilogue of a one-wave GEMM moves the whole output through the SM <-> L2 path at once.)
+        whole_tile_done = true;
+        int m_tile, n_tile, split;
+        decode(unit0, m_tile, n_tile, split);
+        const EpiRows rw = rows_of(m_tile, lg);
+        if (use_tab) fill_coltab(m_tile, n_tile, true);
+        uint8_t* wstg = smem + ew * DEEP_WARP_STG;
+        const int my_n = (n_chunks - par + 1) / 2;   // chunks par, par + 2, ... of this lane group
+        const bool fuse = !split_fast;
+        const bool res_smem = fuse && p.residual && p.res_tma;
+        mbar_wait(&acc_full[0], 0);
+        tc_fence_after();
+        if (threadIdx.x == 64) SDB_TR(6, clock64() - clk0);
+        if (res_smem && lane == 0) {
+          int nload = 0;
+          for (int k = 0; k < my_n; ++k)
+            if (n_tile * BN + (par + 2 * k) * 32 < n_lim) ++nload;
+          if (nload) mbar_arrive_expect_tx(&res_bar[ew], nload * 4096);
+          for (int k = 0; k < my_n; ++k) {
+            const int oc = n_tile * BN + (par + 2 * k) * 32;
+            if (oc < n_lim) tma_load_5d(wstg + k * 4096, &tm.res, &res_bar[ew], oc, rw.sx, rw.sy, rw.sn, 0);
+          }
+        }
+        const uint32_t taddr = tmem_d + (static_cast<uint32_t>(lg * 32) << 16);
+        const bool w32 = split_fast || p.out_f32;
+        const bool w16 = !split_fast && p.out_f16;
+        const bool w16lo = w16 && p.out_f16_lo;
+        const uint32_t vmask = __ballot_sync(0xffffffffu, rw.valid);
+        bool res_ready = false;
+        // one chunk: registers -> fused epilogue -> staging tiles (k = index of the chunk inside this warp)
+        auto process = [&](uint32_t (&rr)[32], int k) {
+          const int c = par + 2 * k;
+          const int ocol0 = n_tile * BN + c * 32;
+          if (ocol0 >= n_lim) return;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
+          uint8_t* s32 = wstg + k * 4096;
+          uint8_t* s16 = st32 ? wstg + 16384 + k * 2048 : wstg + k * 4096;
+          uint8_t* s16l = s16 + 2048;
+          if (fuse) {
+            const float4* tp = reinterpret_cast<const float4*>(coltab + (lg >= 2 ? BN : 0) + c * 32);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 t = tp[q];
+              v[4 * q] = fmaf(v[4 * q], p.alpha, t.x);
+              v[4 * q + 1] = fmaf(v[4 * q + 1], p.alpha, t.y);
+              v[4 * q + 2] = fmaf(v[4 * q + 2], p.alpha, t.z);
+              v[4 * q + 3] = fmaf(v[4 * q + 3], p.alpha, t.w);
+            }
+            if (p.film && !p.film_table) {
+              const float4* fp = reinterpret_cast<const float4*>(p.film + static_cast<size_t>(rw.sample) * p.ldf + ocol0);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                float4 t = __ldg(fp + q);
+                v[4 * q] += t.x;
+                v[4 * q + 1] += t.y;
+                v[4 * q + 2] += t.z;
+                v[4 * q + 3] += t.w;
+              }
+            }
+            if (p.residual) {
+              if (res_smem) {
+                if (!res_ready) {
+                  mbar_wait(&res_bar[ew], 0);
+                  res_ready = true;
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  const float4 t = *reinterpret_cast<const float4*>(s32 + lane * 128 + ((q ^ (lane & 7)) << 4));
+                  v[4 * q] += t.x;
+                  v[4 * q + 1] += t.y;
+                  v[4 * q + 2] += t.z;
+                  v[4 * q + 3] += t.w;
+                }
+              } else if (rw.valid) {
+                const float4* rp = reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(rw.row) * p.ldr + ocol0);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  const float4 t = rp[q];
+                  v[4 * q] += t.x;
+                  v[4 * q + 1] += t.y;
+                  v[4 * q + 2] += t.z;
+                  v[4 * q + 3] += t.w;
+                }
+              }
+            }
+            if (p.act != SDB_ACT_NONE) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+            }
+          }
+          if (w32) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<float4*>(s32 + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+                  make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          }
+          if (w16) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              __half2 h[4];
+              uint4 u, ul;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[8 * q + 2 * e], v[8 * q + 2 * e + 1]);
+              u.x = *reinterpret_cast<uint32_t*>(&h[0]);
+              u.y = *reinterpret_cast<uint32_t*>(&h[1]);
+              u.z = *reinterpret_cast<uint32_t*>(&h[2]);
+              u.w = *reinterpret_cast<uint32_t*>(&h[3]);
+              const uint32_t off = lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4);
+              *reinterpret_cast<uint4*>(s16 + off) = u;
+              if (w16lo) {
+                __half2 l[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float2 hf = __half22float2(h[e]);
+                  l[e] = __floats2half2_rn(v[8 * q + 2 * e] - hf.x, v[8 * q + 2 * e + 1] - hf.y);
+                }
+                ul.x = *reinterpret_cast<uint32_t*>(&l[0]);
+                ul.y = *reinterpret_cast<uint32_t*>(&l[1]);
+                ul.z = *reinterpret_cast<uint32_t*>(&l[2]);
+                ul.w = *reinterpret_cast<uint32_t*>(&l[3]);
+                *reinterpret_cast<uint4*>(s16l + off) = ul;
+              }
+            }
+          }
+        };
+        // GroupNorm partial sums of one staged fp32 chunk (see emit() for the access pattern)
+        auto chunk_stats = [&](int k) {
+          const int c = par + 2 * k;
+          if (n_tile * BN + c * 32 >= n_lim) return;
+          const uint8_t* s32 = wstg + k * 4096;
+          const int gq = lane & 7, rb = lane >> 3;
+          float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const int r = rb + 4 * kk;
+            float4 x = *reinterpret_cast<const float4*>(s32 + r * 128 + ((gq ^ (r & 7)) << 4));
+            const float keep = ((vmask >> r) & 1u) ? 1.0f : 0.0f;
+            x.x *= keep;
+            x.y *= keep;
+            x.z *= keep;
+            x.w *= keep;
+            cs[0] += x.x;
+            cs[1] += x.y;
+            cs[2] += x.z;
+            cs[3] += x.w;
+            cq[0] = fmaf(x.x, x.x, cq[0]);
+            cq[1] = fmaf(x.y, x.y, cq[1]);
+            cq[2] = fmaf(x.z, x.z, cq[2]);
+            cq[3] = fmaf(x.w, x.w, cq[3]);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 8);
+            cq[j] += __shfl_xor_sync(0xffffffffu, cq[j], 8);
+            cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 16);
+            cq[j] += __shfl_xor_sync(0xffffffffu, cq[j], 16);
+          }
+          if (lane < 8) {
+            const int cl = c * 32 + 4 * gq;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<float2*>(&colsum[(lg * BN + cl + j) * 2]) = make_float2(cs[j], cq[j]);
+          }
+        };
+        const bool do_stats = fuse && p.stats && w32 && !(p.dbg & 1);
+#pragma unroll 1
+        for (int k0 = 0; k0 < my_n; k0 += 2) {
+          const bool two = k0 + 1 < my_n;
+          uint32_t ra[32], rb2[32];
+          tmem_ld32(taddr + (par + 2 * k0) * 32, ra);
+          if (two) tmem_ld32(taddr + (par + 2 * k0 + 2) * 32, rb2);
+          tmem_ld_wait();
+          const bool stamp = p.trace && (p.dbg & 64) && threadIdx.x == 64 && k0 == 0;
+          if (stamp) SDB_TR(3, clock64() - clk0);
+          process(ra, k0);
+          if (two) process(rb2, k0 + 1);
+          if (stamp) SDB_TR(4, clock64() - clk0);
+          fence_proxy_async();
+          __syncwarp();
+          if (stamp) SDB_TR(5, clock64() - clk0);
+          if (lane == 0 && !(p.dbg & 4)) {
+            for (int k = k0; k < k0 + (two ? 2 : 1); ++k) {
+              const int oc = n_tile * BN + (par + 2 * k) * 32;
+              if (oc >= n_lim) continue;
+              const uint8_t* s32 = wstg + k * 4096;
+              const uint8_t* s16 = st32 ? wstg + 16384 + k * 2048 : wstg + k * 4096;
+              if (split_fast) {
+                tma_store_5d(&tm.ows, s32, oc, rw.sx, rw.sy, rw.sn, split);
+              } else {
+                if (w32) tma_store_5d(&tm.o32, s32, oc, rw.sx, rw.sy, rw.sn, 0);
+                if (w16) tma_store_5d(&tm.o16, s16, oc, rw.sx, rw.sy, rw.sn, 0);
+                if (w16lo) tma_store_5d(&tm.o16lo, s16 + 2048, oc, rw.sx, rw.sy, rw.sn, 0);
+              }
+            }
+            tma_store_commit();
+          }
+          if (do_stats) {
+            chunk_stats(k0);
+            if (two) chunk_stats(k0 + 1);
+          }
+          if (stamp) SDB_TR(2, clock64() - clk0);
+        }
+        tc_fence_before();
+        if (p.stats && !p.ws && !(p.dbg & 2)) flush_stats(m_tile, n_tile);
+      }
+    }
     uint32_t local = 0;
-    for (int u = unit0; u < n_units; u += ustride, ++local) {
+    for (int u = unit0; u < n_units && !whole_tile_done; u += ustride, ++local) {
       int m_tile, n_tile, split;
       decode(u, m_tile, n_tile, split);
       const uint32_t ab = local & 1;
@@ -810,6 +1040,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
           ocol0 = n_tile * BN + c * 32;
         }
+        tr_chunk = p.trace && (p.dbg & 64) && threadIdx.x == 64 && local == 0 && c == par;
+        if (tr_chunk) SDB_TR(3, clock64() - clk0);
         if (c == last_c) release_acc(ab);
         if (!p.fast) {
           // scalar transposed path (row pitch not TMA-addressable); split-K partials are finished by
@@ -1423,6 +1655,8 @@ extern "C" int sdb_gemm(const sdb_gemm_desc* d, sdb_stream_t stream) {
   tm.o16 = tm.b;
   tm.o16lo = tm.b;
   tm.ows = tm.b;
+  tm.res = tm.b;
+  p.res_tma = 0;
   if (fast) {
     const uint32_t bnn = static_cast<uint32_t>(32 / (p.bw * p.bh));
     auto make_out = [&](CUtensorMap* m, const void* base, int elem, int ncols, long ld, int nsplit) -> int {
@@ -1454,6 +1688,10 @@ extern "C" int sdb_gemm(const sdb_gemm_desc* d, sdb_stream_t stream) {
     if (p.out_f32 && make_out(&tm.o32, p.out_f32, 4, n_out, p.ldo, 1)) return 1;
     if (p.out_f16 && make_out(&tm.o16, p.out_f16, 2, n_out, p.ldo, 1)) return 1;
     if (p.out_f16_lo && make_out(&tm.o16lo, p.out_f16_lo, 2, n_out, p.ldo, 1)) return 1;
+    if (p.residual && !geglu) {
+      if (make_out(&tm.res, p.residual, 4, d->n, p.ldr, 1)) return 1;
+      p.res_tma = 1;
+    }
   }
   // fused GroupNorm statistics: per-tile partial sums of the fp32 output, stored by the epilogue
   p.stats = nullptr;

@@ -265,6 +265,9 @@ def _attn_ref(q, k, v, scale, causal=False):
     (2, 8, 256, 256, 160, 192, False, 1.0), (2, 8, 64, 64, 160, 192, False, 1.0), (2, 8, 4096, 77, 40, 64, False, 1.0),
     (3, 8, 1024, 77, 80, 128, False, 1.0), (2, 12, 77, 77, 64, 64, True, 1.0), (1, 8, 1024, 1024, 40, 64, False, 6.0),
     (1, 2, 200, 333, 64, 64, False, 3.0),
+    # split-state kernel (dpad 64, d < 64): a fully masked column half, ragged tiles, small / large head dims
+    (1, 2, 100, 20, 40, 64, False, 1.0), (1, 2, 130, 45, 56, 64, False, 2.0), (1, 4, 64, 64, 8, 64, False, 1.0),
+    (1, 2, 300, 97, 40, 64, True, 1.0),
 ])
 def test_attention(S, cuda_dev, B, H, nq, nkv, d, dpad, causal, amp):
     g = torch.Generator().manual_seed(nq + nkv + d)
