@@ -30,6 +30,32 @@ VAE_DEC_GF = 2514.5             # per image @ 512x512
 CLIP_GF_PER_PROMPT = 13.0
 
 
+def gemm_dram_traffic():
+    """DRAM bytes per gemm_tc launch from the committed ncu capture of one UNet evaluation (dram__bytes_read.sum +
+    dram__bytes_write.sum per launch, `ncu --metrics ... -k regex:gemm_tc python scripts/profile_unet.py`): newest round
+    first. Returns (bytes per launch or None, source file, launches in the capture)."""
+    import csv
+    for name in ("r02_gemm_dram.csv", "r01_gemm_dram.csv"):
+        path = os.path.join(ROOT, "profiles", name)
+        if not os.path.exists(path):
+            continue
+        try:
+            rows = [r for r in csv.reader(l for l in open(path) if l.startswith('"'))]
+            hdr = rows[0]
+            i_id, i_name, i_unit, i_val = hdr.index("ID"), hdr.index("Metric Name"), hdr.index("Metric Unit"), hdr.index("Metric Value")
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            tot, ids = 0.0, set()
+            for r in rows[1:]:
+                if r[i_name].startswith("dram__bytes_"):
+                    tot += float(r[i_val].replace(",", "")) * scale.get(r[i_unit], 1.0)
+                    ids.add(r[i_id])
+            if ids:
+                return tot / len(ids), "profiles/" + name, len(ids)
+        except Exception:
+            continue
+    return None, None, 0
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -112,15 +138,29 @@ def run_reference(args):
     t_eval = sum(times) / len(times)
     import ldm_oracle as O
     from sdb200 import arch
+    # the rest of an image, timed for real once: AutoencoderKL decode of a 64x64 latent (512x512 image) and the CLIP text
+    # encode of [uncond; prompt]
     vsd = arch.random_state_dict(arch.vae_param_shapes(arch.SD_V1_VAE), 12)
-    z = torch.randn(1, 4, 32, 32, generator=torch.Generator().manual_seed(1))
+    z = torch.randn(1, 4, 64, 64, generator=torch.Generator().manual_seed(1))
     with torch.no_grad():
         t0 = time.perf_counter()
         O.decode_first_stage(vsd, z)
-        t_dec = (time.perf_counter() - t0) * 4.0   # 256x256 sample, decoder cost scales with pixel count
-    value = 1.0 / (51 * t_eval + t_dec)
-    sample = (f"per step: 1 UNet eval N_s=2 @64x64 fp32 ({t_eval:.2f} s); VAE decode 256x256 x4 once ({t_dec:.1f} s); "
-              "image time = 51*eval + decode")
+        t_dec = time.perf_counter() - t0
+    t_clip = 0.0
+    try:
+        csd = arch.random_state_dict(arch.clip_param_shapes(arch.SD_V1_CLIP), 13)
+        ids = torch.randint(0, 49406, (2, 77), generator=torch.Generator().manual_seed(2))
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            O.clip_text(csd, ids, arch.SD_V1_CLIP["num_attention_heads"])
+            t_clip = time.perf_counter() - t0
+    except Exception as ex:   # the CLIP port is optional for the CPU arm; the decode and the UNet evaluations dominate
+        t_clip = 0.0
+        print(f"bench.py: CLIP leg of the CPU arm skipped ({ex!r})", file=sys.stderr)
+    value = 1.0 / (51 * t_eval + t_dec + t_clip)
+    sample = (f"per step: 1 guided UNet eval N_s=2 @64x64 fp32 ({t_eval:.2f} s, bounded sample of the 51 per image); once: "
+              f"AutoencoderKL decode 64x64 -> 512x512 ({t_dec:.1f} s) and CLIP encode of 2x77 tokens ({t_clip:.2f} s); "
+              "image time = 51*eval + decode + clip")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * t_eval, "higher_is_better": True, "scaling": "weak",
@@ -275,11 +315,13 @@ def run_gpu(args):
         n = len(recs)
         pk = peaks()
         ach = fl / (ms * 1e-3) / 1e12
+        traffic, traffic_src, traffic_n = gemm_dram_traffic()
         roof = {"kernel": "gemm_tc_kernel (tcgen05 GEMM / implicit 3x3 conv, all tile shapes) + its split-K epilogue",
                 "bound": "tensor", "achieved": ach, "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
-                "frac": ach / pk["tensor_sustained"], "traffic": 15.06e6,
-                "traffic_note": "ncu dram__bytes_read+write summed over the 210 gemm_tc launches of one UNet evaluation / 210 "
-                                "(profiles/r01_gemm_dram.csv); algorithmic bytes per launch ~9.1 MB (weights 1.72 GB + operands)",
+                "frac": ach / pk["tensor_sustained"], "traffic": traffic,
+                "traffic_note": f"ncu dram__bytes_read+write summed over the {traffic_n} gemm_tc launches of one UNet evaluation "
+                                f"/ {traffic_n}, read at run time from {traffic_src}; algorithmic bytes per launch ~9.1 MB "
+                                "(weights 1.72 GB + operands)",
                 "peak_source": pk["source"] + ", sustained bf16", "launches_per_unet_eval": n,
                 "kernels_per_unet_eval": int(gemm_kernels),
                 "algorithmic_gflop_per_launch": fl / n / 1e9, "avg_launch_us": 1000.0 * ms / n,

@@ -47,4 +47,11 @@ if "c5" in which:
     init = torch.rand(B, 3, 768, 768, generator=torch.Generator().manual_seed(0)).to(dev) * 2 - 1
     ms = timed(lambda: p(init, i, u), reps=1)
     out["C5_img2img_768_b4"] = {"ms_per_batch": ms, "images_per_s": B / ms * 1e3, "achieved_tflops": B * 167.6 / (ms * 1e-3)}
+import os
+os.makedirs("gpurun_out", exist_ok=True)
+meta = {"gpu": torch.cuda.get_device_name(0), "weights": "random-init SD-v1 (seeded)", "timing": "CUDA events around the public "
+        "pipeline call (CLIP encode -> sampler loop -> VAE decode [-> uint8]), inputs resident in HBM, 1 warm-up call"}
+for key, tag in (("C3_txt2img_ddim50_b32", "r02_c3"), ("C4_per_gpu_txt2img_plms50_b8", "r02_c4_per_gpu"), ("C5_img2img_768_b4", "r02_c5")):
+    if key in out:
+        json.dump({"config": key, **out[key], **meta}, open(f"gpurun_out/{tag}.json", "w"), indent=1)
 print(json.dumps(out))

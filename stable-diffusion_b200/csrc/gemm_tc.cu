@@ -1012,6 +1012,56 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       int last_c = -1;
       for (int c = par; c < n_chunks; c += 2) last_c = c;
       if (last_c < 0) release_acc(ab);  // BN = 32: the odd-parity warps own no chunk but still take part in the hand-off
+      if (geglu && p.fast && !p.out_f32 && !p.out_f16_lo) {
+        // GEGLU tiles (fp16 output): value and gate halves of a chunk are two TMEM loads. The loads of this warp's NEXT
+        // chunk are issued as soon as the current chunk is packed to fp16 (16 registers): they are in flight during the
+        // staging, fence and bulk store of the current one - and while the tensor pipe, which owns the TMEM port while it
+        // accumulates the next tile (K is short here: 5-20 steps), keeps them waiting.
+        uint32_t xr[32], gr[32];
+        if (par < n_chunks) {
+          tmem_ld32(taddr + par * 32, xr);
+          tmem_ld32(taddr + HALF + par * 32, gr);
+        }
+#pragma unroll 1
+        for (int c = par; c < n_chunks; c += 2) {
+          uint32_t hp[16];
+          tmem_ld_wait();
+          const float* tb = coltab + c * 32;   // bias of the value half; gate half at +HALF
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float x0 = fmaf(__uint_as_float(xr[2 * j]), p.alpha, tb[2 * j]);
+            const float g0 = fmaf(__uint_as_float(gr[2 * j]), p.alpha, tb[HALF + 2 * j]);
+            const float x1 = fmaf(__uint_as_float(xr[2 * j + 1]), p.alpha, tb[2 * j + 1]);
+            const float g1 = fmaf(__uint_as_float(gr[2 * j + 1]), p.alpha, tb[HALF + 2 * j + 1]);
+            const __half2 h = __floats2half2_rn(x0 * gelu_erf(g0), x1 * gelu_erf(g1));
+            hp[j] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+          if (c == last_c) {
+            release_acc(ab);
+          } else {
+            tmem_ld32(taddr + (c + 2) * 32, xr);
+            tmem_ld32(taddr + HALF + (c + 2) * 32, gr);
+          }
+          const int ocol0 = n_tile * HALF + c * 32;
+          if (ocol0 < n_lim) {
+            uint8_t* s16 = stg + (flip & 1) * 4096;
+            if (lane == 0) tma_store_wait_read<1>();   // the bulk store that last read this staging buffer is done with it
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              *reinterpret_cast<uint4*>(s16 + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) =
+                  make_uint4(hp[4 * q], hp[4 * q + 1], hp[4 * q + 2], hp[4 * q + 3]);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0 && !(p.dbg & 4)) {
+              tma_store_5d(&tm.o16, s16, ocol0, rw.sx, rw.sy, rw.sn, 0);
+              tma_store_commit();
+            }
+            ++flip;
+          }
+        }
+        continue;
+      }
 #pragma unroll 1
       for (int c = par; c < n_chunks; c += 2) {
         float v[32];
