@@ -553,6 +553,265 @@ __global__ void __launch_bounds__(SPLIT_THREADS, 2)
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Wide single-head variant: d = 512 (the AutoencoderKL mid-block AttnBlock, ldm/modules/diffusionmodules/model.py:178-202:
+// softmax(q k^T / sqrt(c)) v over h*w tokens with c = 512 channels). The reference - and the first version of this
+// engine - materialise the N x N logits (64 MiB fp32 per 512^2 image, 324 MiB at 768^2); here they never leave the SM:
+//   * one CTA = 128 query rows x ONE 256-column slice of the output (grid.y = 2 slices; S is recomputed per slice:
+//     the accumulator O of a 512-wide head does not fit the 512 TMEM columns next to S);
+//   * Q (128 x 512 fp16 = 128 KB) stays resident in shared memory as eight 64-column panels; K streams through a ring of
+//     64 x 64 panels, S(j) = sum over the eight panels (32 MMAs, K = 16 each) into a double-buffered TMEM tile;
+//   * V^T slice tiles [256 x 64] and the fp16 P tile are single-buffered (shared memory is full), released by PV(j-1);
+//   * softmax / lazy rescale / epilogue as in attention_tc_kernel (one query row per thread).
+constexpr int WIDE_D = 512;
+constexpr int WIDE_DV = 256;
+constexpr int WIDE_KST = 4;                      // K panel ring depth
+constexpr int WIDE_PANELS = WIDE_D / 64;
+constexpr int WIDE_SMEM = AQ * WIDE_D * 2 + WIDE_KST * (AKV * 64 * 2) + WIDE_DV * AKV * 2 + AQ * AKV * 2 + 1024;
+
+__global__ void __launch_bounds__(192, 1)
+    attention_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                          const __grid_constant__ CUtensorMap tmV, const AttnArgs p) {
+  constexpr int Q_BYTES = AQ * WIDE_D * 2;
+  constexpr int KP_BYTES = AKV * 64 * 2;          // one K panel
+  constexpr int V_BYTES = WIDE_DV * AKV * 2;
+  constexpr int TMEM_COLS = 512;
+  constexpr uint32_t O_COL = 128;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* q_s = smem;
+  uint8_t* k_s = q_s + Q_BYTES;
+  uint8_t* v_s = k_s + WIDE_KST * KP_BYTES;
+  uint8_t* p_s = v_s + V_BYTES;
+
+  __shared__ uint64_t q_full, k_full[WIDE_KST], k_empty[WIDE_KST], v_full, s_full[2], p_full, pv_done;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  const int q0 = blockIdx.x * AQ;
+  const int dv0 = blockIdx.y * WIDE_DV;
+  const int b = blockIdx.z;
+  const int n_iter = (p.nkv + AKV - 1) / AKV;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(&q_full, 1);
+    for (int i = 0; i < WIDE_KST; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+    }
+    mbar_init(&v_full, 1);
+    mbar_init(&s_full[0], 1);
+    mbar_init(&s_full[1], 1);
+    mbar_init(&p_full, 128);
+    mbar_init(&pv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_smem, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_smem;
+
+  pdl_wait();
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(&q_full, Q_BYTES);
+      for (int pn = 0; pn < WIDE_PANELS; ++pn) tma_load_3d(q_s + pn * (AQ * 128), &tmQ, &q_full, pn * 64, q0, b);
+      int ks = 0;
+      uint32_t kph = 0;
+      for (int j = 0; j < n_iter; ++j) {
+        for (int pn = 0; pn < WIDE_PANELS; ++pn) {
+          mbar_wait(&k_empty[ks], kph ^ 1);
+          mbar_arrive_expect_tx(&k_full[ks], KP_BYTES);
+          tma_load_3d(k_s + ks * KP_BYTES, &tmK, &k_full[ks], pn * 64, j * AKV, b);
+          if (++ks == WIDE_KST) {
+            ks = 0;
+            kph ^= 1;
+          }
+        }
+        if (j > 0) mbar_wait(&pv_done, (j - 1) & 1);   // PV(j-1) has read the single V^T buffer
+        mbar_arrive_expect_tx(&v_full, V_BYTES);
+        tma_load_3d(v_s, &tmV, &v_full, j * AKV, dv0, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc_s = umma_idesc_f16(AQ, AKV);
+      constexpr uint32_t idesc_o = umma_idesc_f16(AQ, WIDE_DV);
+      const uint32_t q_addr = smem_u32(q_s);
+      int ks = 0;
+      uint32_t kph = 0;
+      auto issue_s = [&](int j) {
+        const int s = j & 1;
+        for (int pn = 0; pn < WIDE_PANELS; ++pn) {
+          mbar_wait(&k_full[ks], kph);
+          tc_fence_after();
+          const uint32_t k_addr = smem_u32(k_s + ks * KP_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            uint64_t da = umma_desc_k128(q_addr + pn * (AQ * 128) + kk * 32);
+            uint64_t db = umma_desc_k128(k_addr + kk * 32);
+            umma_f16(tmem + s * AKV, da, db, idesc_s, (pn > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(&k_empty[ks]);
+          if (++ks == WIDE_KST) {
+            ks = 0;
+            kph ^= 1;
+          }
+        }
+        umma_commit(&s_full[s]);
+      };
+      mbar_wait(&q_full, 0);
+      if (n_iter > 0) issue_s(0);
+      for (int j = 0; j < n_iter; ++j) {
+        if (j + 1 < n_iter) issue_s(j + 1);
+        mbar_wait(&p_full, j & 1);
+        mbar_wait(&v_full, j & 1);
+        tc_fence_after();
+        const uint32_t p_addr = smem_u32(p_s);
+        const uint32_t v_addr = smem_u32(v_s);
+#pragma unroll
+        for (int kk = 0; kk < AKV / 16; ++kk) {
+          uint64_t da = umma_desc_k128(p_addr + kk * 32);
+          uint64_t db = umma_desc_k128(v_addr + kk * 32);
+          umma_f16(tmem + O_COL, da, db, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(&pv_done);
+      }
+    }
+  } else {
+    const int lg = warp & 3;
+    const int r = lg * 32 + lane;
+    const int qi = q0 + r;
+    const uint32_t lane_addr = static_cast<uint32_t>(lg * 32) << 16;
+    float m_used = -INFINITY;
+    float l = 0.f;
+    for (int j = 0; j < n_iter; ++j) {
+      const int s = j & 1;
+      mbar_wait(&s_full[s], (j >> 1) & 1);
+      tc_fence_after();
+      float t[AKV];
+      {
+        uint32_t r0[32], r1[32];
+        tmem_ld32(tmem + lane_addr + s * AKV, r0);
+        tmem_ld32(tmem + lane_addr + s * AKV + 32, r1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          t[c] = __uint_as_float(r0[c]);
+          t[32 + c] = __uint_as_float(r1[c]);
+        }
+      }
+      const int kv0 = j * AKV;
+      if (kv0 + AKV > p.nkv) {
+#pragma unroll
+        for (int c = 0; c < AKV; ++c)
+          if (kv0 + c >= p.nkv) t[c] = -INFINITY;
+      }
+      float mx[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mx[i] = t[i];
+#pragma unroll
+      for (int c = 8; c < AKV; ++c) mx[c & 7] = fmaxf(mx[c & 7], t[c]);
+      const float m_blk =
+          fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7]))) * p.scale_log2;
+      if (j == 0) {
+        m_used = m_blk;
+      } else {
+        // the single P / V buffers: PV(j-1) must have finished before P(j) is written anyway, so wait for it here and
+        // rescale O directly when the running maximum moved
+        mbar_wait(&pv_done, (j - 1) & 1);
+        tc_fence_after();
+        const float m_new = fmaxf(m_used, m_blk);
+        const bool need = m_new > m_used + 8.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          const float alpha = need ? exp2f(m_used - m_new) : 1.0f;
+#pragma unroll 1
+          for (int c = 0; c < WIDE_DV / 32; ++c) {
+            uint32_t o[32];
+            tmem_ld32(tmem + lane_addr + O_COL + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(tmem + lane_addr + O_COL + c * 32, o);
+          }
+          tmem_st_wait();
+          l *= alpha;
+          if (need) m_used = m_new;
+        }
+      }
+      float sm[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      const float neg_m = -m_used;
+#pragma unroll
+      for (int c = 0; c < AKV; ++c) {
+        t[c] = fast_exp2(fmaf(t[c], p.scale_log2, neg_m));
+        sm[c & 7] += t[c];
+      }
+      l += ((sm[0] + sm[1]) + (sm[2] + sm[3])) + ((sm[4] + sm[5]) + (sm[6] + sm[7]));
+      uint8_t* prow = p_s + r * 128;
+#pragma unroll
+      for (int c16 = 0; c16 < 8; ++c16) {
+        __half2 h0 = __floats2half2_rn(t[c16 * 8 + 0], t[c16 * 8 + 1]);
+        __half2 h1 = __floats2half2_rn(t[c16 * 8 + 2], t[c16 * 8 + 3]);
+        __half2 h2 = __floats2half2_rn(t[c16 * 8 + 4], t[c16 * 8 + 5]);
+        __half2 h3 = __floats2half2_rn(t[c16 * 8 + 6], t[c16 * 8 + 7]);
+        uint4 u;
+        u.x = *reinterpret_cast<uint32_t*>(&h0);
+        u.y = *reinterpret_cast<uint32_t*>(&h1);
+        u.z = *reinterpret_cast<uint32_t*>(&h2);
+        u.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(prow + ((c16 ^ (r & 7)) << 4)) = u;
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(&p_full);
+    }
+    if (n_iter > 0) {
+      mbar_wait(&pv_done, (n_iter - 1) & 1);
+      tc_fence_after();
+    }
+    const float inv_l = l > 0.f ? 1.0f / l : 0.f;
+    __half* orow = p.out + static_cast<size_t>(b) * p.o_batch_stride + static_cast<size_t>(qi) * p.ldo + dv0;
+#pragma unroll 1
+    for (int c = 0; c < WIDE_DV / 32; ++c) {
+      uint32_t o[32];
+      tmem_ld32(tmem + lane_addr + O_COL + c * 32, o);
+      tmem_ld_wait();
+      if (qi < p.nq && n_iter > 0) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          __half2 h0 = __floats2half2_rn(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
+          __half2 h1 = __floats2half2_rn(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
+          __half2 h2 = __floats2half2_rn(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
+          __half2 h3 = __floats2half2_rn(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
+          uint4 u;
+          u.x = *reinterpret_cast<uint32_t*>(&h0);
+          u.y = *reinterpret_cast<uint32_t*>(&h1);
+          u.z = *reinterpret_cast<uint32_t*>(&h2);
+          u.w = *reinterpret_cast<uint32_t*>(&h3);
+          *reinterpret_cast<uint4*>(orow + c * 32 + i) = u;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, TMEM_COLS);
+  }
+}
+
 template <int DPAD>
 static int launch_attn(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnArgs& p, dim3 grid,
                        cudaStream_t st) {
@@ -575,7 +834,52 @@ using namespace sdb;
 extern "C" int sdb_attention(const sdb_attn_desc* d, sdb_stream_t stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SDB_CHECK(d && d->q && d->k && d->vt && d->out, "sdb_attention: null pointer");
-  SDB_CHECK(d->dpad == 64 || d->dpad == 128 || d->dpad == 192, "sdb_attention: dpad must be 64/128/192 (got %d)",
+  if (d->dpad == WIDE_D) {
+    // single-head d = 512 (AutoencoderKL AttnBlock): q, k [B, n, 512], vt [B, 512, ldvt]
+    SDB_CHECK(d->d == WIDE_D && d->heads == 1 && !d->causal, "sdb_attention: dpad 512 is the single-head d = 512 kernel");
+    SDB_CHECK(d->batch > 0 && d->nq > 0 && d->nkv > 0, "sdb_attention: bad sizes");
+    SDB_CHECK(d->ldq % 8 == 0 && d->ldk % 8 == 0 && d->ldvt % 8 == 0 && d->ldo % 8 == 0 && d->o_batch_stride % 8 == 0,
+              "sdb_attention: leading dims must be multiples of 8");
+    CUtensorMap tq, tk, tv;
+    {
+      uint64_t dims[3] = {WIDE_D, static_cast<uint64_t>(d->nq), static_cast<uint64_t>(d->batch)};
+      uint64_t str[2] = {static_cast<uint64_t>(d->ldq) * 2, static_cast<uint64_t>(d->q_batch_stride) * 2};
+      uint32_t box[3] = {64, AQ, 1};
+      if (make_tmap_f16(&tq, d->q, 3, dims, str, box)) return 1;
+    }
+    {
+      uint64_t dims[3] = {WIDE_D, static_cast<uint64_t>(d->nkv), static_cast<uint64_t>(d->batch)};
+      uint64_t str[2] = {static_cast<uint64_t>(d->ldk) * 2, static_cast<uint64_t>(d->k_batch_stride) * 2};
+      uint32_t box[3] = {64, AKV, 1};
+      if (make_tmap_f16(&tk, d->k, 3, dims, str, box)) return 1;
+    }
+    {
+      uint64_t dims[3] = {static_cast<uint64_t>(d->nkv), WIDE_D, static_cast<uint64_t>(d->batch)};
+      uint64_t str[2] = {static_cast<uint64_t>(d->ldvt) * 2, static_cast<uint64_t>(d->vt_batch_stride) * 2};
+      uint32_t box[3] = {AKV, WIDE_DV, 1};
+      if (make_tmap_f16(&tv, d->vt, 3, dims, str, box)) return 1;
+    }
+    AttnArgs p{};
+    p.nq = d->nq;
+    p.nkv = d->nkv;
+    p.d = d->d;
+    p.heads = 1;
+    p.ldo = d->ldo;
+    p.o_batch_stride = d->o_batch_stride;
+    p.out = static_cast<__half*>(d->out);
+    p.scale_log2 = d->scale * 1.4426950408889634f;
+    p.causal = 0;
+    static bool configured = false;
+    if (!configured) {
+      SDB_CUDA(cudaFuncSetAttribute(attention_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WIDE_SMEM));
+      configured = true;
+    }
+    dim3 grid((d->nq + AQ - 1) / AQ, WIDE_D / WIDE_DV, d->batch);
+    SDB_CUDA(launch_pdl(attention_wide_kernel, grid, dim3(192), WIDE_SMEM, st, tq, tk, tv, p));
+    SDB_LAUNCH_CHECK();
+    return 0;
+  }
+  SDB_CHECK(d->dpad == 64 || d->dpad == 128 || d->dpad == 192, "sdb_attention: dpad must be 64/128/192/512 (got %d)",
             d->dpad);
   SDB_CHECK(d->d > 0 && d->d <= d->dpad && d->d % 2 == 0, "sdb_attention: bad head dim %d", d->d);
   SDB_CHECK(d->batch > 0 && d->heads > 0 && d->nq > 0 && d->nkv > 0, "sdb_attention: bad sizes");

@@ -182,6 +182,17 @@ class AutoencoderKL(nn.Module):
         hn, _ = ops.groupnorm(x, *a["gn"], eps=1e-6, silu=False)
         q_all, _ = ops.gemm(hn, a["w_q"], bias=a["b_q"], want_f16=True)           # [nb*n, c]
         k_all, _ = ops.gemm(hn, a["w_k"], bias=a["b_k"], want_f16=True)
+        if c == 512 and n % 8 == 0:
+            # d = 512 flash kernel: the N x N logits stay on the SM (sdb_attention, dpad 512); V^T for the whole batch comes
+            # straight out of the tensor cores (operand roles swapped), one strided view per image
+            vt, _ = ops.gemm(a["w_v"], hn.view(nb * n, c), want_f16=True, b_dynamic=True)      # [c, nb*n]
+            vt3 = vt.view(c, nb, n).permute(1, 0, 2)
+            o = ops.attention(q_all.view(nb, n, c), k_all.view(nb, n, c), vt3, heads=1, d=c, dpad=c, nq=n, nkv=n,
+                              scale=float(int(c) ** -0.5))
+            _, out = ops.gemm(o.view(-1, c), a["w_o"], bias=a["b_o"], residual=x.view(-1, c), want_f32=True,
+                              rows_per_sample=n, want_stats=True, stats_group=_sg(c))
+            return out.view(nb, H, Wd, c)
+        # other widths (test configurations): logits through the GEMM kernel, one image at a time
         o = torch.empty((nb, n, c), dtype=torch.float16, device=x.device)
         npad = (n + 7) // 8 * 8
         for b in range(nb):

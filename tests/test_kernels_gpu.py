@@ -293,6 +293,25 @@ def test_attention(S, cuda_dev, B, H, nq, nkv, d, dpad, causal, amp):
     assert err < 2e-3, err
 
 
+@pytest.mark.parametrize("B,n,amp", [(1, 4096, 1.0), (2, 1024, 3.0), (1, 200, 1.0), (3, 64, 1.0)])
+def test_attention_wide_d512(S, cuda_dev, B, n, amp):
+    """Single-head d = 512 flash kernel (AutoencoderKL AttnBlock, model.py:178-202) against the materialised softmax."""
+    c = 512
+    g = torch.Generator().manual_seed(n)
+    q = (torch.randn(B, n, c, generator=g) * amp).half()
+    k = (torch.randn(B, n, c, generator=g) * amp).half()
+    v = torch.randn(B, n, c, generator=g).half()
+    scale = c ** -0.5
+    ref = torch.softmax(torch.einsum("bid,bjd->bij", q.float(), k.float()) * scale, -1) @ v.float()
+    ld = (n + 7) // 8 * 8
+    vt = torch.zeros(B, c, ld, dtype=torch.float16)
+    vt[:, :, :n] = v.transpose(1, 2)
+    out = S.ops.attention(q.to(cuda_dev), k.to(cuda_dev), vt.to(cuda_dev), heads=1, d=c, dpad=c, nq=n, nkv=n, scale=scale)
+    torch.cuda.synchronize()
+    err = rel_l2(out.float().cpu(), ref)
+    assert err < 2e-3, err
+
+
 @pytest.mark.parametrize("nb,h,w,c0,c1,silu,eps", [
     (2, 16, 16, 320, 0, True, 1e-5), (2, 8, 8, 1280, 1280, True, 1e-5), (2, 32, 32, 640, 320, False, 1e-6),
     (1, 64, 64, 128, 0, True, 1e-6), (2, 16, 16, 1280, 640, True, 1e-5),
