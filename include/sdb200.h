@@ -242,6 +242,61 @@ int sdb_pointwise_small(const float* x, int64_t npix, int32_t cin, int32_t cout,
 int sdb_embed_tokens(const int64_t* ids, int32_t rows, int32_t n_ctx, int32_t dim, int32_t vocab, const float* tok,
                      const float* pos, float* out, sdb_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Handle-level entry points: the engine, not just its kernels.
+ *
+ * A plan is the ordered list of sdb_* launches of one pass over the model, recorded (arguments copied by value) while
+ * the host side walks the model once between sdb_plan_begin and sdb_plan_end - the calls still execute, so the
+ * recording pass doubles as the warm-up. sdb_plan_launch replays it as ONE CUDA graph (captured on first use on a
+ * private stream). Every pointer inside is a caller-owned static buffer (weights, workspaces, I/O) that must outlive
+ * the plan. Recording is per host thread.
+ */
+typedef struct sdb_plan sdb_plan;
+int sdb_plan_begin(sdb_plan** out);
+int sdb_plan_end(sdb_plan* plan);
+int sdb_plan_size(const sdb_plan* plan);                 /* recorded launches (-1: NULL) */
+int sdb_plan_run(sdb_plan* plan, sdb_stream_t stream);    /* eager replay, call by call */
+int sdb_plan_launch(sdb_plan* plan, sdb_stream_t stream); /* graph replay */
+int sdb_plan_destroy(sdb_plan* plan);
+int sdb_fill_f32(float* x, int64_t n, float value, sdb_stream_t stream);
+
+/*
+ * One guided UNet evaluation as a handle: replaces sampler -> LatentDiffusion.apply_model -> DiffusionWrapper.forward
+ * -> UNetModel.forward (ldm/models/diffusion/ddpm.py:891-992,1393-1421; ldm/modules/diffusionmodules/openaimodel.py:
+ * 710-742). `plan` was recorded over one evaluation whose first kernel reads x_static [n, c_in, h, w] (NCHW fp32) and
+ * t_static [n] and whose last kernel writes eps_static [n, c_out, h, w]; the cross-attention context is baked into the
+ * plan (its K / V buffers are static: re-fill them to change the prompt). sdb_unet_forward copies x / t in when they
+ * are not the static buffers themselves (NULL = already in place), launches the graph and copies eps out (NULL = leave
+ * it in eps_static).
+ */
+typedef struct sdb_unet sdb_unet;
+int sdb_unet_create(sdb_plan* plan, float* x_static, float* t_static, float* eps_static, int32_t n, int32_t c_in,
+                    int32_t c_out, int32_t h, int32_t w, sdb_unet** out);
+int sdb_unet_forward(sdb_unet* unet, const float* x, const float* t, float* eps, sdb_stream_t stream);
+int sdb_unet_destroy(sdb_unet* unet);
+
+/*
+ * A whole PLMS trajectory (ldm/models/diffusion/plms.py:98-236, eta = 0) on the device: per step one sdb_unet_forward
+ * (two on the first step: pseudo improved Euler) and one fused sdb_sampler_step. The schedule is passed as host arrays
+ * indexed like the reference's ddim_* arrays (index 0 = the LAST step taken); timesteps are the ddim_timesteps as
+ * floats. `unet` evaluates 2 * batch samples when guided ([uncond; cond] halves of the latent), else batch.
+ */
+typedef struct sdb_plms_desc {
+  sdb_unet* unet;
+  const float* x;          /* x_T, fp32 [batch, c, h, w] (device) */
+  float* x_out;            /* final latent [batch, c, h, w] (device; may alias x) */
+  float* pred_x0_out;      /* optional: last predicted x0 */
+  float* work;             /* device scratch: (5 + 2 * rep) * batch*c*h*w floats, rep = guided ? 2 : 1 */
+  int32_t batch, n_steps, guided;
+  float scale;             /* unconditional_guidance_scale */
+  const float* timesteps;  /* host [n_steps] */
+  const float* alphas;     /* host [n_steps] ddim_alphas */
+  const float* alphas_prev;
+  const float* sqrt_one_minus_alphas;
+  const float* sigmas;     /* host [n_steps] or NULL (eta = 0) */
+} sdb_plms_desc;
+int sdb_sample_plms(const sdb_plms_desc* d, sdb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

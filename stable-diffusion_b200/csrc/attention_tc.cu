@@ -832,6 +832,10 @@ static int launch_attn(const CUtensorMap& q, const CUtensorMap& k, const CUtenso
 using namespace sdb;
 
 extern "C" int sdb_attention(const sdb_attn_desc* d, sdb_stream_t stream) {
+  if (d && ::sdb::plan_recording()) {
+    const sdb_attn_desc c = *d;
+    ::sdb::plan_record([c](cudaStream_t s_) { return sdb_attention(&c, s_); });
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SDB_CHECK(d && d->q && d->k && d->vt && d->out, "sdb_attention: null pointer");
   if (d->dpad == WIDE_D) {

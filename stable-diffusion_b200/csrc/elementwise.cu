@@ -283,6 +283,7 @@ using namespace sdb;
 
 extern "C" int sdb_nchw_to_nhwc(const float* x, int32_t nb, int32_t c, int32_t hw, float* out_f32, void* out_f16,
                                 sdb_stream_t stream) {
+  SDB_REC(sdb_nchw_to_nhwc(x, nb, c, hw, out_f32, out_f16, s_));
   SDB_CHECK(x && (out_f32 || out_f16), "sdb_nchw_to_nhwc: null pointer");
   dim3 grid((hw + 31) / 32, (c + 31) / 32, nb), block(32, 8);
   nchw_to_nhwc_kernel<<<grid, block, 0, ST>>>(x, c, hw, out_f32, static_cast<__half*>(out_f16));
@@ -290,6 +291,7 @@ extern "C" int sdb_nchw_to_nhwc(const float* x, int32_t nb, int32_t c, int32_t h
   return 0;
 }
 extern "C" int sdb_nhwc_to_nchw(const float* x, int32_t nb, int32_t c, int32_t hw, float* out, sdb_stream_t stream) {
+  SDB_REC(sdb_nhwc_to_nchw(x, nb, c, hw, out, s_));
   SDB_CHECK(x && out, "sdb_nhwc_to_nchw: null pointer");
   dim3 grid((hw + 31) / 32, (c + 31) / 32, nb), block(32, 8);
   nhwc_to_nchw_kernel<<<grid, block, 0, ST>>>(x, c, hw, out);
@@ -299,6 +301,7 @@ extern "C" int sdb_nhwc_to_nchw(const float* x, int32_t nb, int32_t c, int32_t h
 extern "C" int sdb_im2col3x3(const float* x, int32_t nb, int32_t h, int32_t w, int32_t c, int32_t stride,
                              int32_t pad_lo, int32_t ho, int32_t wo, int32_t kpad, void* out_f16,
                              sdb_stream_t stream) {
+  SDB_REC(sdb_im2col3x3(x, nb, h, w, c, stride, pad_lo, ho, wo, kpad, out_f16, s_));
   SDB_CHECK(x && out_f16 && kpad >= 9 * c && kpad % 64 == 0, "sdb_im2col3x3: bad arguments (kpad=%d c=%d)", kpad, c);
   size_t total = static_cast<size_t>(nb) * ho * wo * kpad;
   im2col3x3_kernel<<<grid_for(total), 256, 0, ST>>>(x, nb, h, w, c, stride, pad_lo, ho, wo, kpad,
@@ -308,6 +311,7 @@ extern "C" int sdb_im2col3x3(const float* x, int32_t nb, int32_t h, int32_t w, i
 }
 extern "C" int sdb_upsample2x(const float* x, int32_t nb, int32_t h, int32_t w, int32_t c, void* out_f16,
                               sdb_stream_t stream) {
+  SDB_REC(sdb_upsample2x(x, nb, h, w, c, out_f16, s_));
   SDB_CHECK(x && out_f16 && c % 4 == 0, "sdb_upsample2x: bad arguments");
   size_t total = static_cast<size_t>(nb) * 4 * h * w * (c / 4);
   upsample2x_kernel<<<grid_for(total), 256, 0, ST>>>(x, nb, h, w, c, static_cast<__half*>(out_f16));
@@ -315,12 +319,14 @@ extern "C" int sdb_upsample2x(const float* x, int32_t nb, int32_t h, int32_t w, 
   return 0;
 }
 extern "C" int sdb_cast_f16(const float* x, int64_t n, void* out_f16, sdb_stream_t stream) {
+  SDB_REC(sdb_cast_f16(x, n, out_f16, s_));
   SDB_CHECK(x && out_f16 && n >= 0, "sdb_cast_f16: bad arguments");
   cast_f16_kernel<<<grid_for(n), 256, 0, ST>>>(x, static_cast<size_t>(n), static_cast<__half*>(out_f16));
   SDB_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int sdb_silu_f16(const float* x, int64_t n, void* out_f16, sdb_stream_t stream) {
+  SDB_REC(sdb_silu_f16(x, n, out_f16, s_));
   SDB_CHECK(x && out_f16 && n >= 0, "sdb_silu_f16: bad arguments");
   silu_f16_kernel<<<grid_for(n), 256, 0, ST>>>(x, static_cast<size_t>(n), static_cast<__half*>(out_f16));
   SDB_LAUNCH_CHECK();
@@ -328,6 +334,7 @@ extern "C" int sdb_silu_f16(const float* x, int64_t n, void* out_f16, sdb_stream
 }
 extern "C" int sdb_transpose_f16(const void* x, int32_t batch, int32_t rows, int32_t cols, int32_t ldx, void* out,
                                  int32_t ldo, sdb_stream_t stream) {
+  SDB_REC(sdb_transpose_f16(x, batch, rows, cols, ldx, out, ldo, s_));
   SDB_CHECK(x && out && ldx >= cols && ldo >= rows, "sdb_transpose_f16: bad arguments");
   dim3 grid((rows + 31) / 32, (cols + 31) / 32, batch), block(32, 8);
   transpose_f16_kernel<<<grid, block, 0, ST>>>(static_cast<const __half*>(x), rows, cols, ldx,
@@ -337,6 +344,7 @@ extern "C" int sdb_transpose_f16(const void* x, int32_t batch, int32_t rows, int
 }
 extern "C" int sdb_timestep_embedding(const float* t, int32_t n, int32_t dim, float max_period, void* out_f16,
                                       sdb_stream_t stream) {
+  SDB_REC(sdb_timestep_embedding(t, n, dim, max_period, out_f16, s_));
   SDB_CHECK(t && out_f16 && dim % 2 == 0, "sdb_timestep_embedding: bad arguments");
   timestep_embedding_kernel<<<grid_for(static_cast<size_t>(n) * dim / 2), 256, 0, ST>>>(
       t, n, dim, max_period, static_cast<__half*>(out_f16));
@@ -348,6 +356,7 @@ extern "C" int sdb_sampler_step(const float* x, const float* eps2, const float* 
                                 const float* h1, const float* h2, const float* h3, const float* noise, float a_t,
                                 float a_prev, float sigma_t, float sqrt_one_minus_a_t, int64_t n, float* x_prev,
                                 float* x_prev2, float* pred_x0, float* e_out, sdb_stream_t stream) {
+  SDB_REC(sdb_sampler_step(x, eps2, eps_cond, guided, scale, order, h1, h2, h3, noise, a_t, a_prev, sigma_t, sqrt_one_minus_a_t, n, x_prev, x_prev2, pred_x0, e_out, s_));
   SDB_CHECK(x && eps2 && n > 0, "sdb_sampler_step: bad arguments");
   SDB_CHECK(order >= 0 && order <= 4, "sdb_sampler_step: order %d", order);
   SDB_CHECK((order == 0) || h1, "sdb_sampler_step: missing history");
@@ -363,6 +372,7 @@ extern "C" int sdb_dpm_solver_step(const float* x, const float* eps2, const floa
                                    float alpha_s, int32_t order, const float* m_prev, float c_x, float c_m,
                                    float inv_r0, int64_t n, float* m_out, float* x_out, float* x_out2,
                                    sdb_stream_t stream) {
+  SDB_REC(sdb_dpm_solver_step(x, eps2, eps_cond, guided, scale, sigma_s, alpha_s, order, m_prev, c_x, c_m, inv_r0, n, m_out, x_out, x_out2, s_));
   SDB_CHECK(x && eps2 && x_out && n > 0, "sdb_dpm_solver_step: bad arguments");
   SDB_CHECK(order == 1 || (order == 2 && m_prev), "sdb_dpm_solver_step: order %d (2 needs the previous prediction)", order);
   if (!eps_cond) eps_cond = eps2 + n;
@@ -373,6 +383,7 @@ extern "C" int sdb_dpm_solver_step(const float* x, const float* eps2, const floa
 }
 extern "C" int sdb_mask_blend(const float* img_orig, const float* mask, int32_t mask_channels, int32_t nb, int32_t c,
                               int64_t hw, float* img, float* img2, sdb_stream_t stream) {
+  SDB_REC(sdb_mask_blend(img_orig, mask, mask_channels, nb, c, hw, img, img2, s_));
   SDB_CHECK(img_orig && mask && img && nb > 0 && c > 0 && hw > 0, "sdb_mask_blend: bad arguments");
   SDB_CHECK(mask_channels == 1 || mask_channels == c, "sdb_mask_blend: mask has %d channels, latent %d", mask_channels, c);
   const size_t n = static_cast<size_t>(nb) * c * hw;
@@ -383,6 +394,7 @@ extern "C" int sdb_mask_blend(const float* img_orig, const float* mask, int32_t 
 }
 extern "C" int sdb_vae_sample(const float* moments, const float* noise_nchw, int32_t nb, int32_t hw,
                               float scale_factor, float* z_nchw, sdb_stream_t stream) {
+  SDB_REC(sdb_vae_sample(moments, noise_nchw, nb, hw, scale_factor, z_nchw, s_));
   SDB_CHECK(moments && z_nchw, "sdb_vae_sample: null pointer");
   vae_sample_kernel<<<grid_for(static_cast<size_t>(nb) * 4 * hw), 256, 0, ST>>>(moments, noise_nchw, nb, hw,
                                                                                 scale_factor, z_nchw);
@@ -390,6 +402,7 @@ extern "C" int sdb_vae_sample(const float* moments, const float* noise_nchw, int
   return 0;
 }
 extern "C" int sdb_to_uint8(const float* x, int64_t n, uint8_t* out, sdb_stream_t stream) {
+  SDB_REC(sdb_to_uint8(x, n, out, s_));
   SDB_CHECK(x && out, "sdb_to_uint8: null pointer");
   to_uint8_kernel<<<grid_for(n), 256, 0, ST>>>(x, static_cast<size_t>(n), out);
   SDB_LAUNCH_CHECK();
@@ -397,12 +410,14 @@ extern "C" int sdb_to_uint8(const float* x, int64_t n, uint8_t* out, sdb_stream_
 }
 extern "C" int sdb_axpby2(const float* x, const float* y, float a, float b, int64_t n, float* out,
                           sdb_stream_t stream) {
+  SDB_REC(sdb_axpby2(x, y, a, b, n, out, s_));
   SDB_CHECK(x && y && out, "sdb_axpby2: null pointer");
   axpby2_kernel<<<grid_for(n), 256, 0, ST>>>(x, y, a, b, static_cast<size_t>(n), out);
   SDB_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int sdb_axpby(const float* x, float a, float b, int64_t n, float* out, sdb_stream_t stream) {
+  SDB_REC(sdb_axpby(x, a, b, n, out, s_));
   SDB_CHECK(x && out, "sdb_axpby: null pointer");
   axpby_kernel<<<grid_for(n), 256, 0, ST>>>(x, a, b, static_cast<size_t>(n), out);
   SDB_LAUNCH_CHECK();
@@ -410,6 +425,7 @@ extern "C" int sdb_axpby(const float* x, float a, float b, int64_t n, float* out
 }
 extern "C" int sdb_pointwise_small(const float* x, int64_t npix, int32_t cin, int32_t cout, const float* w,
                                    const float* b, float alpha, float* out, sdb_stream_t stream) {
+  SDB_REC(sdb_pointwise_small(x, npix, cin, cout, w, b, alpha, out, s_));
   SDB_CHECK(x && w && out && cin > 0 && cin <= 16 && cout > 0 && cout <= 16, "sdb_pointwise_small: bad arguments");
   pointwise_small_kernel<<<grid_for(static_cast<size_t>(npix) * cout), 256, 0, ST>>>(
       x, static_cast<size_t>(npix), cin, cout, w, b, alpha, out);
@@ -418,6 +434,7 @@ extern "C" int sdb_pointwise_small(const float* x, int64_t npix, int32_t cin, in
 }
 extern "C" int sdb_embed_tokens(const int64_t* ids, int32_t rows, int32_t n_ctx, int32_t dim, int32_t vocab,
                                 const float* tok, const float* pos, float* out, sdb_stream_t stream) {
+  SDB_REC(sdb_embed_tokens(ids, rows, n_ctx, dim, vocab, tok, pos, out, s_));
   SDB_CHECK(ids && tok && pos && out, "sdb_embed_tokens: null pointer");
   embed_tokens_kernel<<<grid_for(static_cast<size_t>(rows) * dim), 256, 0, ST>>>(
       reinterpret_cast<const long long*>(ids), rows, n_ctx, dim, vocab, tok, pos, out);

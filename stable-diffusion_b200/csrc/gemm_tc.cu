@@ -1575,6 +1575,10 @@ extern "C" int sdb_gemm_plan(const sdb_gemm_desc* d, int32_t* out) {
 }
 
 extern "C" int sdb_gemm(const sdb_gemm_desc* d, sdb_stream_t stream) {
+  if (d && ::sdb::plan_recording()) {
+    const sdb_gemm_desc c = *d;
+    ::sdb::plan_record([c](cudaStream_t s_) { return sdb_gemm(&c, s_); });
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SDB_CHECK(d && d->a0 && d->b, "sdb_gemm: null operand");
   SDB_CHECK(d->taps == 1 || d->taps == 9, "sdb_gemm: taps must be 1 or 9 (got %d)", d->taps);

@@ -4,7 +4,18 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <functional>
+
 namespace sdb {
+
+// plan recording (plan.cu): while a plan is being recorded on this thread every launching entry point also appends a
+// closure that repeats the call on another stream
+bool plan_recording();
+void plan_record(std::function<int(cudaStream_t)> fn);
+#define SDB_REC(call_with_stream_s_)                                                        \
+  do {                                                                                      \
+    if (::sdb::plan_recording()) ::sdb::plan_record([=](cudaStream_t s_) { return call_with_stream_s_; }); \
+  } while (0)
 
 // Last error string for the C-ABI (sdb_last_error). Thread-local: one engine per process/device.
 void set_error(const char* fmt, ...);

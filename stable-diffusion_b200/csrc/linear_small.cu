@@ -118,6 +118,7 @@ using namespace sdb;
 
 extern "C" int sdb_linear_small(const float* x, int32_t m, int32_t k, const void* w_f16, int32_t n, const float* bias,
                                 int32_t act, float* out_f32, void* out_f16, sdb_stream_t stream) {
+  SDB_REC(sdb_linear_small(x, m, k, w_f16, n, bias, act, out_f32, out_f16, s_));
   SDB_CHECK(x && w_f16 && (out_f32 || out_f16), "sdb_linear_small: null pointer");
   SDB_CHECK(k % 8 == 0 && m > 0 && n > 0, "sdb_linear_small: k must be a multiple of 8 (got %d)", k);
   SDB_CHECK((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_f16) & 15) == 0,
@@ -139,6 +140,7 @@ extern "C" int sdb_linear_small(const float* x, int32_t m, int32_t k, const void
 
 extern "C" int sdb_timestep_embedding_f32(const float* t, int32_t n, int32_t dim, float max_period, float* out,
                                           sdb_stream_t stream) {
+  SDB_REC(sdb_timestep_embedding_f32(t, n, dim, max_period, out, s_));
   SDB_CHECK(t && out && dim % 2 == 0, "sdb_timestep_embedding_f32: bad arguments");
   int total = n * dim / 2;
   timestep_embedding_f32_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(t, n, dim,

@@ -432,6 +432,7 @@ extern "C" int sdb_groupnorm(const float* x0, const float* x1, int32_t c0, int32
                              void* out_f16, void* raw_f16, void* out_lo_f16, void* raw_lo_f16, void* stats_ws,
                              const void* chan_stats0, const void* chan_stats1, int32_t stats_t0, int32_t stats_t1,
                              int32_t stats_group, sdb_stream_t stream) {
+  SDB_REC(sdb_groupnorm(x0, x1, c0, c1, nb, hw, groups, gamma, beta, eps, silu, out_f16, raw_f16, out_lo_f16, raw_lo_f16, stats_ws, chan_stats0, chan_stats1, stats_t0, stats_t1, stats_group, s_));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int C = c0 + c1;
   SDB_CHECK(x0 && out_f16 && stats_ws && gamma && beta, "sdb_groupnorm: null pointer");
@@ -493,6 +494,7 @@ extern "C" int sdb_groupnorm(const float* x0, const float* x1, int32_t c0, int32
 
 extern "C" int sdb_layernorm(const float* x, int32_t rows, int32_t c, const float* gamma, const float* beta, float eps,
                              void* out_f16, float* out_f32, sdb_stream_t stream) {
+  SDB_REC(sdb_layernorm(x, rows, c, gamma, beta, eps, out_f16, out_f32, s_));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SDB_CHECK(x && gamma && beta && (out_f16 || out_f32), "sdb_layernorm: null pointer");
   SDB_CHECK(c <= 32 * 48, "sdb_layernorm: C=%d too large", c);
@@ -531,6 +533,7 @@ extern "C" int sdb_layernorm(const float* x, int32_t rows, int32_t c, const floa
 
 extern "C" int sdb_softmax_rows(const float* x, int32_t rows, int32_t cols, float scale, void* out_f16,
                                 sdb_stream_t stream) {
+  SDB_REC(sdb_softmax_rows(x, rows, cols, scale, out_f16, s_));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SDB_CHECK(x && out_f16, "sdb_softmax_rows: null pointer");
   softmax_rows_kernel<<<rows, 256, 0, st>>>(x, cols, scale, static_cast<__half*>(out_f16));

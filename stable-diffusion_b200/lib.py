@@ -62,6 +62,15 @@ class AttnDesc(C.Structure):
     ]
 
 
+class PlmsDesc(C.Structure):
+    _fields_ = [
+        ("unet", C.c_void_p), ("x", C.c_void_p), ("x_out", C.c_void_p), ("pred_x0_out", C.c_void_p), ("work", C.c_void_p),
+        ("batch", C.c_int32), ("n_steps", C.c_int32), ("guided", C.c_int32), ("scale", C.c_float),
+        ("timesteps", C.POINTER(C.c_float)), ("alphas", C.POINTER(C.c_float)), ("alphas_prev", C.POINTER(C.c_float)),
+        ("sqrt_one_minus_alphas", C.POINTER(C.c_float)), ("sigmas", C.POINTER(C.c_float)),
+    ]
+
+
 _P, _I, _L, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
 # name -> argtypes; every symbol declared in include/sdb200.h must appear here (tests check both ways).
@@ -96,6 +105,18 @@ SIGNATURES = {
     "sdb_dpm_solver_step": ([_P, _P, _P, _I, _F, _F, _F, _I, _P, _F, _F, _F, _L, _P, _P, _P, _P], C.c_int),
     "sdb_mask_blend": ([_P, _P, _I, _I, _I, _L, _P, _P, _P], C.c_int),
     "sdb_axpby2": ([_P, _P, _F, _F, _L, _P, _P], C.c_int),
+    # handle level (plan.cu)
+    "sdb_plan_begin": ([C.POINTER(C.c_void_p)], C.c_int),
+    "sdb_plan_end": ([_P], C.c_int),
+    "sdb_plan_size": ([_P], C.c_int),
+    "sdb_plan_run": ([_P, _P], C.c_int),
+    "sdb_plan_launch": ([_P, _P], C.c_int),
+    "sdb_plan_destroy": ([_P], C.c_int),
+    "sdb_fill_f32": ([_P, _L, _F, _P], C.c_int),
+    "sdb_unet_create": ([_P, _P, _P, _P, _I, _I, _I, _I, _I, C.POINTER(C.c_void_p)], C.c_int),
+    "sdb_unet_forward": ([_P, _P, _P, _P, _P], C.c_int),
+    "sdb_unet_destroy": ([_P], C.c_int),
+    "sdb_sample_plms": ([C.POINTER(PlmsDesc), _P], C.c_int),
 }
 
 _lib = None

@@ -217,12 +217,11 @@ def _tune_gemm(d, M, n, rps, stats_ok, stats_group):
     st = _stream()
     keep = (d.block_n, d.pair, d.splits, d.splitk_mode, d.stats_out)
     scratch = None
-    if stats_ok:   # large enough for any candidate's slot count (<= one slot per 32 rows)
-        scratch = torch.empty((M // rps) * max(1, rps // 32) * (n // stats_group) * 2 + 16, dtype=torch.float32,
-                              device=torch.device("cuda", torch.cuda.current_device()))
-        d.stats_out = _ptr(scratch)
+    if stats_ok:
+        d.stats_out = C.c_void_p(16)     # placeholder while the candidates are planned (sized below)
     plan = (C.c_int32 * 5)()
     cands = []
+    max_slots = 1
     for bn in (64, 128, 160, 256):
         pad = (n + bn - 1) // bn * bn - n
         if bn > 64 and pad >= bn // 2:
@@ -240,6 +239,13 @@ def _tune_gemm(d, M, n, rps, stats_ok, stats_group):
                 if (plan[0], plan[1], plan[2], plan[3]) != (bn, cg, sp, mode if sp > 1 else 0):
                     continue
                 cands.append((bn, cg, sp, mode))
+                max_slots = max(max_slots, int(plan[4]))
+    if stats_ok:
+        # the statistics slots per sample depend on the candidate (tiles x cluster splits, or one per 32 rows with the
+        # workspace epilogue): size the scratch for the largest one - a smaller buffer is overrun by the epilogues
+        scratch = torch.empty((M // rps) * max_slots * (n // stats_group) * 2 + 16, dtype=torch.float32,
+                              device=torch.device("cuda", torch.cuda.current_device()))
+        d.stats_out = _ptr(scratch)
     best, best_t = None, float("inf")
     for cand in cands:
         d.block_n, d.pair, d.splits, d.splitk_mode = cand

@@ -472,6 +472,41 @@ class UNetModel(nn.Module):
             self._graphs[shape] = g
         return g
 
+    # ------------------------------------------------------------------ handle-level C entry (include/sdb200.h)
+    @torch.no_grad()
+    def c_handle(self, shape, context):
+        """Build the C-side handle of one guided evaluation for latents of `shape` = (n, c, h, w) and the given context:
+        walks the model once between sdb_plan_begin / sdb_plan_end (every launch is recorded with its arguments; the
+        pass doubles as warm-up), then wraps the plan and its static x / t / eps buffers in an sdb_unet. Afterwards
+        `sdb_unet_forward(handle, x, t, eps, stream)` and `sdb_sample_plms` run without any Python on the hot path.
+        All intermediates of the recorded pass live in a private memory pool owned by the returned object."""
+        import ctypes as C
+        from . import lib as _l
+        lib = _l.load()
+        dev = self.W["device"]
+        kvs = self.set_context(context)
+        x = torch.zeros(shape, dtype=torch.float32, device=dev)
+        t = torch.zeros((shape[0],), dtype=torch.float32, device=dev)
+        ops.AUTOTUNE = self.autotune
+        try:
+            self._forward_impl(x, t, kvs)       # (block_n, split-K) selection happens outside the recording
+        finally:
+            ops.AUTOTUNE = False
+        torch.cuda.synchronize()
+        pool = torch.cuda.MemPool()
+        plan = C.c_void_p()
+        with torch.cuda.use_mem_pool(pool):
+            _l.check(lib.sdb_plan_begin(C.byref(plan)), "sdb_plan_begin")
+            try:
+                eps = self._forward_impl(x, t, kvs)
+            finally:
+                _l.check(lib.sdb_plan_end(plan), "sdb_plan_end")
+        torch.cuda.synchronize()
+        h = C.c_void_p()
+        _l.check(lib.sdb_unet_create(plan, C.c_void_p(x.data_ptr()), C.c_void_p(t.data_ptr()), C.c_void_p(eps.data_ptr()),
+                                     shape[0], shape[1], eps.shape[1], shape[2], shape[3], C.byref(h)), "sdb_unet_create")
+        return CUNet(h, plan, pool, (x, t, eps, kvs, context), int(lib.sdb_plan_size(plan)))
+
     @torch.no_grad()
     def forward(self, x, timesteps=None, context=None, y=None, **kwargs):
         assert y is None, "must specify y if and only if the model is class-conditional"
@@ -501,3 +536,63 @@ class UNetModel(nn.Module):
         t = timesteps.to(torch.float32).contiguous()
         eps = self._forward_impl(x.contiguous().float(), t, kvs)
         return eps.to(x.dtype)
+
+
+class CUNet:
+    """Owner of an sdb_unet handle (include/sdb200.h): the C plan, its CUDA graph and the memory pool holding every
+    intermediate buffer of the recorded evaluation."""
+
+    def __init__(self, handle, plan, pool, keep, n_launches):
+        self.handle, self.plan, self.pool, self.keep, self.n_launches = handle, plan, pool, keep, n_launches
+        self.x, self.t, self.eps = keep[0], keep[1], keep[2]
+
+    def forward(self, x, t, out=None):
+        """eps = UNet(x, t) through sdb_unet_forward on the current stream (x, t: fp32 cuda tensors)."""
+        import ctypes as C
+        from . import lib as _l
+        lib = _l.load()
+        if out is None:
+            out = torch.empty_like(self.eps)
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _l.check(lib.sdb_unet_forward(self.handle, C.c_void_p(x.data_ptr()), C.c_void_p(t.data_ptr()),
+                                      C.c_void_p(out.data_ptr()), st), "sdb_unet_forward")
+        return out
+
+    def sample_plms(self, x_T, sampler, scale, guided=True):
+        """Whole PLMS trajectory in C (sdb_sample_plms) with the schedule of an sdb200 PLMSSampler on which
+        make_schedule() has been called. Returns (x_0 latent, pred_x0)."""
+        import ctypes as C
+        import numpy as np
+        from . import lib as _l
+        lib = _l.load()
+        b = x_T.shape[0]
+        rep = 2 if guided else 1
+        per = x_T.numel()
+        work = torch.empty((5 + 2 * rep) * per, dtype=torch.float32, device=x_T.device)
+        x_out, p0 = torch.empty_like(x_T), torch.empty_like(x_T)
+        arr = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+        ts, al, ap = arr(sampler.ddim_timesteps), arr(sampler.ddim_alphas), arr(sampler.ddim_alphas_prev)
+        sq, sg = arr(sampler.ddim_sqrt_one_minus_alphas), arr(sampler.ddim_sigmas)
+        fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+        d = _l.PlmsDesc()
+        d.unet, d.x, d.x_out, d.pred_x0_out, d.work = self.handle, x_T.data_ptr(), x_out.data_ptr(), p0.data_ptr(), work.data_ptr()
+        d.batch, d.n_steps, d.guided, d.scale = b, len(ts), 1 if guided else 0, float(scale)
+        d.timesteps, d.alphas, d.alphas_prev, d.sqrt_one_minus_alphas, d.sigmas = fp(ts), fp(al), fp(ap), fp(sq), fp(sg)
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _l.check(lib.sdb_sample_plms(C.byref(d), st), "sdb_sample_plms")
+        torch.cuda.current_stream().synchronize()   # the host schedule arrays and `work` must outlive the enqueued work
+        return x_out, p0
+
+    def close(self):
+        from . import lib as _l
+        if self.handle is not None:
+            lib = _l.load()
+            lib.sdb_unet_destroy(self.handle)
+            lib.sdb_plan_destroy(self.plan)
+            self.handle = self.plan = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -46,13 +46,32 @@ def test_struct_layouts_match_header():
                 continue
             names = decl.replace("*", " ").split()
             # "int32_t c0, c1, c2, c3" -> several names
-            first = [n for n in names if n not in ("const", "void", "float", "int32_t", "int64_t")]
+            first = [n for n in names if n not in ("const", "void", "float", "int32_t", "int64_t", "sdb_unet")]
             out += [n.strip(",") for n in first]
         return out
 
     assert fields("sdb_gemm_desc") == [f[0] for f in sdb200.lib.GemmDesc._fields_]
     assert fields("sdb_attn_desc") == [f[0] for f in sdb200.lib.AttnDesc._fields_]
     assert ctypes.sizeof(sdb200.lib.GemmDesc) % 8 == 0
+    assert fields("sdb_plms_desc") == [f[0] for f in sdb200.lib.PlmsDesc._fields_]
+
+
+def test_plan_recording_lifecycle_without_gpu():
+    """Handle-level entry points: a plan can be opened, closed and destroyed without a device; launching an empty or
+    unrecorded plan is an error with a message, not a crash."""
+    lib = sdb200.lib.load()
+    plan = ctypes.c_void_p()
+    assert lib.sdb_plan_begin(ctypes.byref(plan)) == 0 and plan.value
+    other = ctypes.c_void_p()
+    assert lib.sdb_plan_begin(ctypes.byref(other)) != 0          # one recording per thread
+    assert b"already" in lib.sdb_last_error()
+    assert lib.sdb_plan_launch(plan, None) != 0                   # still open
+    assert lib.sdb_plan_end(plan) == 0
+    assert lib.sdb_plan_size(plan) == 0
+    assert lib.sdb_plan_launch(plan, None) != 0                   # empty
+    h = ctypes.c_void_p()
+    assert lib.sdb_unet_create(plan, None, None, None, 2, 4, 4, 8, 8, ctypes.byref(h)) != 0
+    assert lib.sdb_plan_destroy(plan) == 0
 
 
 def test_product_path_fails_loudly_without_cuda():
