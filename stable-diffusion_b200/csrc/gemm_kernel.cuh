@@ -269,12 +269,14 @@ struct EpiRows {   // the output rows one epilogue warp handles: row per lane + 
 //   0 lean   : no activation, TMA-store epilogue, bias / FiLM through the column table  (almost every UNet GEMM)
 //   1 geglu  : GEGLU with fp16 output only (the feed-forward up-projection)
 //   2 general: everything (activations, scalar-store epilogue for odd widths, per-row FiLM, fp32 + fp16 hi/lo outputs)
+//   3 lean + cluster split-K (kind 0 is compiled without the cluster exchange, kind 3 without the single-CTA epilogue)
 template <int BN, int CG, bool DEEP, int KIND>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TmapPack tm, const GemmArgs p) {
   // compile-time specialisation of the descriptor fields the KIND fixes (dead branches fold away)
-  const int act = KIND == 0 ? SDB_ACT_NONE : (KIND == 1 ? SDB_ACT_GEGLU : p.act);
+  const int act = (KIND == 0 || KIND == 3) ? SDB_ACT_NONE : (KIND == 1 ? SDB_ACT_GEGLU : p.act);
   const bool fast = KIND == 2 ? (p.fast != 0) : true;
   const bool film_row = KIND == 2 && p.film && !p.film_table;
+  const int csk = KIND == 0 ? 0 : (KIND == 3 ? 1 : p.csk);   // lean kinds: 0 = no cluster split-K, 3 = cluster split-K
   using Cfg = GemmCfg<BN, CG, DEEP>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int B_ROWS = Cfg::B_ROWS;
@@ -304,19 +306,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   const long long clk0 = clock64();
 
   // ---- cluster coordinates. CTA pair: ranks (2k, 2k+1), the even one leads. Cluster split-K: rank / CG = K slice.
-  const bool clustered = (CG == 2) || (p.csk != 0);
+  const bool clustered = (CG == 2) || (csk != 0);
   const uint32_t crank = clustered ? cluster_ctarank() : 0u;
   const uint32_t pr = CG == 2 ? (crank & 1u) : 0u;
   const uint32_t lead = crank - pr;
-  const int csplit = p.csk ? static_cast<int>(crank) / CG : 0;
-  const int n_units = p.m_units * p.n_tiles * (p.csk ? 1 : p.splits);
-  const int unit0 = p.csk ? static_cast<int>(blockIdx.x) / (p.splits * CG) : static_cast<int>(blockIdx.x) / CG;
-  const int ustride = p.csk ? (1 << 30) : static_cast<int>(gridDim.x) / CG;
+  const int csplit = csk ? static_cast<int>(crank) / CG : 0;
+  const int n_units = p.m_units * p.n_tiles * (csk ? 1 : p.splits);
+  const int unit0 = csk ? static_cast<int>(blockIdx.x) / (p.splits * CG) : static_cast<int>(blockIdx.x) / CG;
+  const int ustride = csk ? (1 << 30) : static_cast<int>(gridDim.x) / CG;
   auto decode = [&](int u, int& m_tile, int& n_tile, int& split) {
     const int mu = u % p.m_units;
     const int rest = u / p.m_units;
     n_tile = rest % p.n_tiles;
-    split = p.csk ? csplit : rest / p.n_tiles;
+    split = csk ? csplit : rest / p.n_tiles;
     m_tile = mu * CG + static_cast<int>(pr);
   };
   if (p.trace && threadIdx.x == 0) {
@@ -324,7 +326,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     if (blockIdx.x == 0) {
       p.trace[0] = gridDim.x;
       p.trace[1] = BN + 1000 * CG;
-      p.trace[2] = p.splits + 100 * p.csk;
+      p.trace[2] = p.splits + 100 * csk;
       p.trace[3] = p.k_iters;
       p.trace[4] = p.M;
       p.trace[5] = p.N;
@@ -363,7 +365,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       tmem_relinquish();
     }
   }
-  if (p.csk && p.stats) {   // lane groups this CTA does not own contribute zeros to its statistics
+  if (csk && p.stats) {   // lane groups this CTA does not own contribute zeros to its statistics
     for (int i = threadIdx.x; i < 4 * BN * 2; i += GEMM_THREADS) colsum[i] = 0.f;
   }
   tc_fence_before();
@@ -379,7 +381,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   const int par = ew >> 2;       // the two warps of a lane group alternate chunks
   const int et = threadIdx.x - 64;
   uint8_t* stg = staging + ew * STG_WARP_BYTES;
-  const bool geglu = KIND == 0 ? false : (KIND == 1 ? true : ((p.act == SDB_ACT_GEGLU) && !p.ws));
+  const bool geglu = (KIND == 0 || KIND == 3) ? false : (KIND == 1 ? true : ((p.act == SDB_ACT_GEGLU) && !p.ws));
   constexpr int HALF = BN / 2;
   const int n_chunks = geglu ? HALF / 32 : BN / 32;
   const int n_lim = geglu ? p.N / 2 : p.N;   // output columns that exist
@@ -604,7 +606,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         int t;
         if (p.taps == 1) t = halves == 1 ? (prow % p.rows_per_sample) / BM : 0;
         else t = m_tile % p.stats_tps;   // spatial tile position (each half of a two-sample tile has its own sample)
-        if (p.csk) t = t * p.splits + csplit;
+        if (csk) t = t * p.splits + csplit;
         float a = 0.f, b = 0.f;
         for (int j = 0; j < sg; ++j) {
           const int cl = g * sg + j;
@@ -772,7 +774,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       if (!(p.dbg & 64)) SDB_TR(5, clock64() - clk0);
     }
     __syncwarp();
-  } else if (!p.csk && warp < B_WARP) {
+  } else if (!csk && warp < B_WARP) {
     // epilogue warps 2..9 : TMEM lane group = warp % 4; the two warps of a lane group alternate chunks.
     // Latency plan: everything the fused epilogue reads from global memory is requested BEFORE the accumulator is
     // ready - bias (+ FiLM) of the tile's columns go to a shared-memory table, the residual rows of a chunk are
@@ -791,7 +793,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     };
     bool whole_tile_done = false;
     if constexpr (DEEP) {
-      if (fast && !geglu && (KIND == 0 || !(st32 && st16 && p.out_f16_lo))) {
+      if (fast && !geglu && (KIND == 0 || KIND == 3 || !(st32 && st16 && p.out_f16_lo))) {
         // ---- single-tile epilogue. The CTA owns exactly one tile and the operand ring is idle once the accumulator is
         // complete, so every warp stages ALL its chunks in a private slice of it: the TMEM loads of two chunks are in
         // flight together, the residual tile arrives by TMA (in the swizzled layout of the store boxes - a row-per-thread
@@ -1007,7 +1009,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       }
     }
     uint32_t local = 0;
-    constexpr bool GENERIC_LOOP = !(DEEP && KIND == 0);   // lean single-tile CTAs always take the path above
+    constexpr bool GENERIC_LOOP = !(DEEP && (KIND == 0 || KIND == 3));   // lean single-tile CTAs always take the path above
     for (int u = unit0; GENERIC_LOOP && u < n_units && !whole_tile_done; u += ustride, ++local) {
       int m_tile, n_tile, split;
       decode(u, m_tile, n_tile, split);
@@ -1127,7 +1129,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   }
 
   // ---------------------------------------------------------------- cluster split-K: exchange + owner epilogue
-  if (p.csk) {
+  if (csk) {
     // S K-slices of ONE tile sit in the tensor memories of the cluster's CTAs. Rows are scattered to their owner
     // (K slice o owns lane groups [o * 4/S, (o+1) * 4/S) of its pair-rank's 128 rows) through distributed shared
     // memory into the (now idle) stage ring; the owner sums the S partials in slice order and runs the fused epilogue.
@@ -1373,7 +1375,12 @@ template <int BN, int CG, int KIND>
 static int launch_gemm(const TmapPack& tm, const GemmArgs& p, cudaStream_t st) {
   const int units = p.m_units * p.n_tiles * p.splits;
   const bool deep = p.csk || units <= sm_count() / CG;
-  return deep ? launch_gemm_cfg<BN, CG, true, KIND>(tm, p, st) : launch_gemm_cfg<BN, CG, false, KIND>(tm, p, st);
+  if constexpr (KIND == 3) {
+    SDB_CHECK(deep, "sdb_gemm: cluster split-K launches are single-tile");
+    return launch_gemm_cfg<BN, CG, true, KIND>(tm, p, st);
+  } else {
+    return deep ? launch_gemm_cfg<BN, CG, true, KIND>(tm, p, st) : launch_gemm_cfg<BN, CG, false, KIND>(tm, p, st);
+  }
 }
 
 
@@ -1410,5 +1417,6 @@ static int launch_gemm_kind(int bn, int cg, const TmapPack& tm, const GemmArgs& 
 int launch_gemm_kind0(int bn, int cg, const TmapPack& tm, const GemmArgs& p, cudaStream_t st);
 int launch_gemm_kind1(int bn, int cg, const TmapPack& tm, const GemmArgs& p, cudaStream_t st);
 int launch_gemm_kind2(int bn, int cg, const TmapPack& tm, const GemmArgs& p, cudaStream_t st);
+int launch_gemm_kind3(int bn, int cg, const TmapPack& tm, const GemmArgs& p, cudaStream_t st);
 
 }  // namespace sdb

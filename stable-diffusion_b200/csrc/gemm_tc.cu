@@ -423,8 +423,11 @@ extern "C" int sdb_gemm(const sdb_gemm_desc* d, sdb_stream_t stream) {
   int kind = 2;
   if (p.fast && d->act == SDB_ACT_GEGLU && !p.out_f32 && !p.out_f16_lo && !p.ws) kind = 1;
   else if (p.fast && d->act == SDB_ACT_NONE && (!p.film || p.film_table) && !(p.out_f32 && p.out_f16 && p.out_f16_lo)) kind = 0;
-  int rc = kind == 0 ? launch_gemm_kind0(bn, ch.cg, tm, p, st)
-                     : kind == 1 ? launch_gemm_kind1(bn, ch.cg, tm, p, st) : launch_gemm_kind2(bn, ch.cg, tm, p, st);
+  if (kind == 0 && p.csk) kind = 3;
+  int rc = kind == 0   ? launch_gemm_kind0(bn, ch.cg, tm, p, st)
+           : kind == 1 ? launch_gemm_kind1(bn, ch.cg, tm, p, st)
+           : kind == 3 ? launch_gemm_kind3(bn, ch.cg, tm, p, st)
+                       : launch_gemm_kind2(bn, ch.cg, tm, p, st);
   if (rc) return rc;
   if (splits > 1 && !p.csk) {
     const bool vec = (p.N % 4 == 0) && (p.ldo % 4 == 0) && (!p.residual || p.ldr % 4 == 0) && (!p.film || p.ldf % 4 == 0);
