@@ -69,6 +69,7 @@ struct GemmArgs {
   int cb[MAX_SRC + 1];  // cumulative 64-channel chunk boundaries of the A sources; cb[nsrc] = chunks per tap
   int H, W, NB;
   int TW, TH, TN, tiles_x, tiles_y;
+  int lw, lh;           // log2(TW), log2(TH): the spatial tile sides are powers of two
   int k_iters, iters_per_split, splits;
   int m_tiles, n_tiles;
   int m_units;          // m_tiles for single CTAs, ceil(m_tiles / 2) for CTA pairs
@@ -123,21 +124,38 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   return x;
 }
 
-__device__ __forceinline__ bool map_row(const GemmArgs& p, int m_tile, int r, int& out_row) {
+// Output row of accumulator row r of tile m_tile. 3x3 geometry: a tile is TW x TH x TN output pixels (powers of two, so
+// the row decomposes with shifts); its origin (TileGeo) costs three integer divisions and is computed once per tile.
+struct TileGeo {
+  int gx0, gy0, gn0;
+};
+__device__ __forceinline__ TileGeo tile_geo(const GemmArgs& p, int m_tile) {
+  TileGeo g{0, 0, 0};
+  if (p.taps != 1) {
+    const int t2 = m_tile / p.tiles_x;
+    const int tx = m_tile - t2 * p.tiles_x;
+    const int tn = t2 / p.tiles_y;
+    const int ty = t2 - tn * p.tiles_y;
+    g.gx0 = tx * p.TW;
+    g.gy0 = ty * p.TH;
+    g.gn0 = tn * p.TN;
+  }
+  return g;
+}
+__device__ __forceinline__ bool map_row(const GemmArgs& p, const TileGeo& g, int m_tile, int r, int& out_row) {
   if (p.taps == 1) {
     out_row = m_tile * BM + r;
     return out_row < p.M;
   }
-  int tx = m_tile % p.tiles_x;
-  int t2 = m_tile / p.tiles_x;
-  int ty = t2 % p.tiles_y;
-  int tn = t2 / p.tiles_y;
-  int x = r % p.TW;
-  int y = (r / p.TW) % p.TH;
-  int nl = r / (p.TW * p.TH);
-  int gx = tx * p.TW + x, gy = ty * p.TH + y, gn = tn * p.TN + nl;
+  const int x = r & (p.TW - 1);
+  const int y = (r >> p.lw) & (p.TH - 1);
+  const int nl = r >> (p.lw + p.lh);
+  const int gx = g.gx0 + x, gy = g.gy0 + y, gn = g.gn0 + nl;
   out_row = (gn * p.H + gy) * p.W + gx;
   return gy < p.H && gn < p.NB;
+}
+__device__ __forceinline__ bool map_row(const GemmArgs& p, int m_tile, int r, int& out_row) {
+  return map_row(p, tile_geo(p, m_tile), m_tile, r, out_row);
 }
 
 // One element of the fused epilogue (after alpha/bias which are column-only).
@@ -397,25 +415,25 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 
   auto rows_of = [&](int m_tile, int lgx) {
     EpiRows rw;
-    rw.valid = map_row(p, m_tile, lgx * 32 + lane, rw.row);
+    const TileGeo geo = tile_geo(p, m_tile);
+    rw.valid = map_row(p, geo, m_tile, lgx * 32 + lane, rw.row);
     rw.sample = rw.valid ? rw.row / p.rows_per_sample : 0;
     if (p.taps == 1) {
       rw.sx = m_tile * BM + lgx * 32;
       rw.sy = 0;
       rw.sn = 0;
     } else {
-      const int tx = m_tile % p.tiles_x;
-      const int t2 = m_tile / p.tiles_x;
       const int r0 = lgx * 32;
-      rw.sx = tx * p.TW + r0 % p.TW;
-      rw.sy = (t2 % p.tiles_y) * p.TH + (r0 / p.TW) % p.TH;
-      rw.sn = (t2 / p.tiles_y) * p.TN + r0 / (p.TW * p.TH);
+      rw.sx = geo.gx0 + (r0 & (p.TW - 1));
+      rw.sy = geo.gy0 + ((r0 >> p.lw) & (p.TH - 1));
+      rw.sn = geo.gn0 + (r0 >> (p.lw + p.lh));
     }
     return rw;
   };
   // column table of a tile: bias (+ FiLM of the sample each row half belongs to); all epilogue warps take part
   auto fill_coltab = [&](int m_tile, int n_tile, bool first) {
     if (!first) asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");   // readers of the previous tile's table
+    const TileGeo geo = tile_geo(p, m_tile);
     for (int i = et; i < 2 * BN; i += 32 * EPI_WARPS) {
       const int hsel = i / BN, cl = i - hsel * BN;
       const int col = n_tile * BN + cl;
@@ -424,7 +442,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         if (p.bias) t = __ldg(p.bias + col);
         if (p.film && p.film_table) {
           int prow;
-          if (map_row(p, m_tile, hsel * 64, prow))
+          if (map_row(p, geo, m_tile, hsel * 64, prow))
             t += __ldg(p.film + static_cast<size_t>(prow / p.rows_per_sample) * p.ldf + col);
         }
       }
@@ -596,11 +614,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     const int gpt = BN / sg;       // BN % sg == 0 (checked on the host)
     const int E = p.N / sg;
     const int halves = p.stats_halves;
+    const TileGeo geo = tile_geo(p, m_tile);
     for (int i = et; i < halves * gpt; i += 32 * EPI_WARPS) {
       const int hsel = i / gpt, g = i - hsel * gpt;
       const int col0 = n_tile * BN + g * sg;
       int prow;
-      const bool pv = map_row(p, m_tile, hsel * 64, prow);   // first tile row of this half
+      const bool pv = map_row(p, geo, m_tile, hsel * 64, prow);   // first tile row of this half
       if (pv && col0 < p.N) {
         const int s = prow / p.rows_per_sample;
         int t;
@@ -608,6 +627,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         else t = m_tile % p.stats_tps;   // spatial tile position (each half of a two-sample tile has its own sample)
         if (csk) t = t * p.splits + csplit;
         float a = 0.f, b = 0.f;
+#pragma unroll 1
         for (int j = 0; j < sg; ++j) {
           const int cl = g * sg + j;
           if (halves == 2) {

@@ -280,6 +280,10 @@ extern "C" int sdb_gemm(const sdb_gemm_desc* d, sdb_stream_t stream) {
   p.b_static = d->b_dynamic ? 0 : 1;
   const int n_out = geglu ? d->n / 2 : d->n;
   p.ldo = d->ldo > 0 ? d->ldo : n_out;
+  p.lw = 0;
+  p.lh = 0;
+  while ((1 << p.lw) < g.TW) ++p.lw;
+  while ((1 << p.lh) < g.TH) ++p.lh;
   p.TW = g.TW;
   p.TH = g.TH;
   p.TN = g.TN;

@@ -102,14 +102,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // Bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU box. The poll loop is kept to
 // try_wait + counter (the hardware suspends the thread inside try_wait): waiting warps must not eat the issue slots of
 // the compute warps that share their scheduler.
+// (the report-and-trap path is a separate function: inlined at every wait site it was 5 % of the GEMM kernel's code)
+static __device__ __noinline__ void mbar_timeout(uint32_t bar_addr, uint32_t parity) {
+  printf("sdb: mbarrier wait timeout block(%d,%d,%d) thread %d bar@%u parity %u\n", blockIdx.x, blockIdx.y, blockIdx.z,
+         threadIdx.x, bar_addr, parity);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins == (1u << 24)) {
-      printf("sdb: mbarrier wait timeout block(%d,%d,%d) thread %d bar@%u parity %u\n", blockIdx.x, blockIdx.y,
-             blockIdx.z, threadIdx.x, smem_u32(bar), parity);
-      __trap();
-    }
+    if (++spins == (1u << 24)) mbar_timeout(smem_u32(bar), parity);
   }
 }
 
