@@ -222,11 +222,14 @@ def _tune_gemm(d, M, n, rps, stats_ok, stats_group):
     plan = (C.c_int32 * 5)()
     cands = []
     max_slots = 1
-    for bn in (64, 128, 160, 256):
+    import os
+    bns = tuple(int(v) for v in os.environ.get("SDB_TUNE_BN", "64,128,160,256").split(","))
+    cgs = tuple(int(v) for v in os.environ.get("SDB_TUNE_CG", "1,2").split(","))
+    for bn in bns:
         pad = (n + bn - 1) // bn * bn - n
         if bn > 64 and pad >= bn // 2:
             continue
-        for cg in (1, 2):
+        for cg in cgs:
             for sp, mode in ((1, 0), (2, 2), (4, 2), (2, 1), (3, 1), (4, 1), (6, 1), (8, 1), (12, 1), (16, 1)):
                 if mode == 1 and not d.workspace:
                     continue
