@@ -26,7 +26,8 @@ int sdb_sm_count(void);
 long long sdb_launch_count(void); /* kernels launched through this library since load */
 /* Debug only: subsequent sdb_gemm launches write per-CTA phase timestamps (8-word launch header + 8 words per CTA,
  * 1288 words per launch) into the device buffer `buf` of n_words uint64; NULL switches tracing off. Returns the
- * number of words handed out since the previous call. Used by scripts/timeline_unet.py. */
+ * number of words handed out since the previous call. Used by scripts/timeline_unet.py. The stamps are written only by
+ * a library built with -DSDB_TRACE (SDB_BUILD_TRACE=1 python build.py); the production build leaves the buffer untouched. */
 long long sdb_debug_trace(void* buf, int64_t n_words);
 
 /* ---- epilogue activations ---- */

@@ -19,6 +19,8 @@ FLAGS = [
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
 ]
+if os.environ.get("SDB_BUILD_TRACE"):   # debug build: in-kernel phase stamps (sdb_debug_trace) and SDB_DBG switches
+    FLAGS.append("-DSDB_TRACE")
 
 
 def _newer(target: Path, deps) -> bool:

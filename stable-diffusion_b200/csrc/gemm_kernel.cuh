@@ -250,9 +250,14 @@ __device__ __forceinline__ unsigned long long gtimer() {
   return t;
 }
 // debug trace: word w of this CTA's record (8 words per CTA after an 8-word launch header)
-#define SDB_TR(w, val)                                                          \
-  do {                                                                          \
-    if (p.trace && blockIdx.x < 160) p.trace[8 + blockIdx.x * 8 + (w)] = (val); \
+#ifdef SDB_TRACE
+#define SDB_TRACE_ENABLED 1
+#else
+#define SDB_TRACE_ENABLED 0
+#endif
+#define SDB_TR(w, val)                                                                             \
+  do {                                                                                             \
+    if (SDB_TRACE_ENABLED && trace && blockIdx.x < 160) trace[8 + blockIdx.x * 8 + (w)] = (val);   \
   } while (0)
 
 // DEEP: every CTA computes exactly ONE tile (grid <= resident CTAs, or cluster split-K). The epilogue then starts only
@@ -294,6 +299,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   const int act = (KIND == 0 || KIND == 3) ? SDB_ACT_NONE : (KIND == 1 ? SDB_ACT_GEGLU : p.act);
   const bool fast = KIND == 2 ? (p.fast != 0) : true;
   const bool film_row = KIND == 2 && p.film && !p.film_table;
+  // debug hooks (phase stamps, SDB_DBG switches) exist only in a -DSDB_TRACE build (SDB_BUILD_TRACE=1 python build.py):
+  // in the production kernel they were 8 % of the code every launch fetches
+  const int dbg = SDB_TRACE_ENABLED ? p.dbg : 0;
+  unsigned long long* const trace = SDB_TRACE_ENABLED ? p.trace : nullptr;
   const int csk = KIND == 0 ? 0 : (KIND == 3 ? 1 : p.csk);   // lean kinds: 0 = no cluster split-K, 3 = cluster split-K
   using Cfg = GemmCfg<BN, CG, DEEP>;
   constexpr int STAGES = Cfg::STAGES;
@@ -339,17 +348,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     split = csk ? csplit : rest / p.n_tiles;
     m_tile = mu * CG + static_cast<int>(pr);
   };
-  if (p.trace && threadIdx.x == 0) {
+  if (trace && threadIdx.x == 0) {
     SDB_TR(0, gtimer());
     if (blockIdx.x == 0) {
-      p.trace[0] = gridDim.x;
-      p.trace[1] = BN + 1000 * CG;
-      p.trace[2] = p.splits + 100 * csk;
-      p.trace[3] = p.k_iters;
-      p.trace[4] = p.M;
-      p.trace[5] = p.N;
-      p.trace[6] = p.taps;
-      p.trace[7] = n_units;
+      trace[0] = gridDim.x;
+      trace[1] = BN + 1000 * CG;
+      trace[2] = p.splits + 100 * csk;
+      trace[3] = p.k_iters;
+      trace[4] = p.M;
+      trace[5] = p.N;
+      trace[6] = p.taps;
+      trace[7] = n_units;
     }
   }
 
@@ -391,7 +400,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = tmem_base_smem;
-  if (threadIdx.x == 0 && !(p.dbg & 64)) SDB_TR(2, clock64() - clk0);
+  if (threadIdx.x == 0 && !(dbg & 64)) SDB_TR(2, clock64() - clk0);
 
   // ---------------------------------------------------------------- epilogue state and helpers (warps 2..9)
   const int ew = (warp - 2) & 7;
@@ -553,7 +562,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     fence_proxy_async();
     __syncwarp();
     if (tr_chunk) SDB_TR(5, clock64() - clk0);
-    if (lane == 0 && !(p.dbg & 4)) {
+    if (lane == 0 && !(dbg & 4)) {
       if (raw_partial) {
         tma_store_5d(&tm.ows, s32, ocol0, rw.sx, rw.sy, rw.sn, split);
       } else {
@@ -563,7 +572,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       }
       tma_store_commit();
     }
-    if (!raw_partial && p.stats && w32 && !(p.dbg & 1)) {
+    if (!raw_partial && p.stats && w32 && !(dbg & 1)) {
       // GroupNorm statistics of the value just produced, from the staged 32x32 fp32 tile: lane l reads the 16-byte
       // granule (l & 7) of rows (l >> 3) + 4k (8 independent LDS.128, conflict-free), two butterfly steps fold the four
       // row classes, lanes 0-7 then hold the sums of columns 4*(l & 7) .. +3 and write the CTA's shared column sums
@@ -659,10 +668,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       // round trip into the producer's issue loop).
       const bool is_a = warp == 0;
       const uint32_t full_base = CG == 2 ? mapa_shared(smem_u32(&full_bar[0]), lead) : smem_u32(&full_bar[0]);
-      const uint32_t arm_bytes = (((p.dbg & 8) ? 0u : Cfg::B_BYTES) + ((p.dbg & 32) ? 0u : A_BYTES)) * CG;
+      const uint32_t arm_bytes = (((dbg & 8) ? 0u : Cfg::B_BYTES) + ((dbg & 32) ? 0u : A_BYTES)) * CG;
       const uint32_t smem_base = smem_u32(smem) + (is_a ? 0u : static_cast<uint32_t>(A_BYTES));
       if (is_a || !p.b_static) pdl_wait();
-      if (is_a && !(p.dbg & 64)) SDB_TR(3, clock64() - clk0);
+      if (is_a && !(dbg & 64)) SDB_TR(3, clock64() - clk0);
       int s = 0;
       uint32_t ph = 0;
       bool ring_pass = false;
@@ -701,7 +710,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           if (ring_pass) mbar_wait(&empty_bar[s], ph ^ 1);   // (first pass over the ring: every slot is free)
           if (is_a) {
             if (pr == 0) mbar_arrive_expect_tx(&full_bar[s], arm_bytes);
-            if (!(p.dbg & 32)) {
+            if (!(dbg & 32)) {
               if (CG == 2) tma_load_4d_cg2_addr(dst, amap, bar, c0, x0 + dx, y0 + dy, n0);
               else tma_load_4d_addr(dst, amap, bar, c0, x0 + dx, y0 + dy, n0);
             }
@@ -723,7 +732,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
               amap = &tm.a[src];
             }
           } else {
-            if (!(p.dbg & 8)) {
+            if (!(dbg & 8)) {
               if (CG == 2) tma_load_2d_cg2_addr(dst, &tm.b, bar, kb, nrow);
               else tma_load_2d_addr(dst, &tm.b, bar, kb, nrow);
             }
@@ -767,10 +776,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           if (first_data) {
-            if (!(p.dbg & 64)) SDB_TR(4, clock64() - clk0);
+            if (!(dbg & 64)) SDB_TR(4, clock64() - clk0);
             first_data = false;
           }
-          if (!(p.dbg & 16)) {
+          if (!(dbg & 16)) {
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
               // advance 32 bytes (16 fp16) along K inside the 128-byte swizzle atom: +2 in the (addr>>4) field
@@ -791,7 +800,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         if (CG == 2) umma_commit_cg2(&acc_full[ab], cmask);
         else umma_commit(&acc_full[ab]);
       }
-      if (!(p.dbg & 64)) SDB_TR(5, clock64() - clk0);
+      if (!(dbg & 64)) SDB_TR(5, clock64() - clk0);
     }
     __syncwarp();
   } else if (!csk && warp < B_WARP) {
@@ -986,7 +995,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
               *reinterpret_cast<float2*>(&colsum[(lg * BN + cl + j) * 2]) = make_float2(cs[j], cq[j]);
           }
         };
-        const bool do_stats = fuse && p.stats && w32 && !(p.dbg & 1);
+        const bool do_stats = fuse && p.stats && w32 && !(dbg & 1);
 #pragma unroll 1
         for (int k0 = 0; k0 < my_n; k0 += 2) {
           const bool two = k0 + 1 < my_n;
@@ -994,7 +1003,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           tmem_ld32(taddr + (par + 2 * k0) * 32, ra);
           if (two) tmem_ld32(taddr + (par + 2 * k0 + 2) * 32, rb2);
           tmem_ld_wait();
-          const bool stamp = p.trace && (p.dbg & 64) && threadIdx.x == 64 && k0 == 0;
+          const bool stamp = trace && (dbg & 64) && threadIdx.x == 64 && k0 == 0;
           if (stamp) SDB_TR(3, clock64() - clk0);
           process(ra, k0);
           if (two) process(rb2, k0 + 1);
@@ -1002,7 +1011,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           fence_proxy_async();
           __syncwarp();
           if (stamp) SDB_TR(5, clock64() - clk0);
-          if (lane == 0 && !(p.dbg & 4)) {
+          if (lane == 0 && !(dbg & 4)) {
             for (int k = k0; k < k0 + (two ? 2 : 1); ++k) {
               const int oc = n_tile * BN + (par + 2 * k) * 32;
               if (oc >= n_lim) continue;
@@ -1025,7 +1034,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           if (stamp) SDB_TR(2, clock64() - clk0);
         }
         tc_fence_before();
-        if (p.stats && !p.ws && !(p.dbg & 2)) flush_stats(m_tile, n_tile);
+        if (p.stats && !p.ws && !(dbg & 2)) flush_stats(m_tile, n_tile);
       }
     }
     uint32_t local = 0;
@@ -1087,7 +1096,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                   make_uint4(hp[4 * q], hp[4 * q + 1], hp[4 * q + 2], hp[4 * q + 3]);
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0 && !(p.dbg & 4)) {
+            if (lane == 0 && !(dbg & 4)) {
               tma_store_5d(&tm.o16, s16, ocol0, rw.sx, rw.sy, rw.sn, 0);
               tma_store_commit();
             }
@@ -1124,7 +1133,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
           ocol0 = n_tile * BN + c * 32;
         }
-        tr_chunk = p.trace && (p.dbg & 64) && threadIdx.x == 64 && local == 0 && c == par;
+        tr_chunk = trace && (dbg & 64) && threadIdx.x == 64 && local == 0 && c == par;
         if (tr_chunk) SDB_TR(3, clock64() - clk0);
         if (c == last_c) release_acc(ab);
         if (!fast) {
@@ -1144,7 +1153,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           for (int q = 0; q < 8; ++q) rcur[q] = rnxt[q];
         }
       }
-      if (p.stats && !p.ws && !(p.dbg & 2)) flush_stats(m_tile, n_tile);
+      if (p.stats && !p.ws && !(dbg & 2)) flush_stats(m_tile, n_tile);
     }
   }
 
