@@ -670,8 +670,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       const uint32_t full_base = CG == 2 ? mapa_shared(smem_u32(&full_bar[0]), lead) : smem_u32(&full_bar[0]);
       const uint32_t arm_bytes = (((dbg & 8) ? 0u : Cfg::B_BYTES) + ((dbg & 32) ? 0u : A_BYTES)) * CG;
       const uint32_t smem_base = smem_u32(smem) + (is_a ? 0u : static_cast<uint32_t>(A_BYTES));
-      if (is_a || !p.b_static) pdl_wait();
-      if (is_a && !(dbg & 64)) SDB_TR(3, clock64() - clk0);
+      // the dependency wait sits right before this thread's first load: the tile decode / tap geometry below (cold code with
+      // integer divisions) overlaps the predecessor's tail instead of following it
+      bool need_wait = is_a || !p.b_static;
       int s = 0;
       uint32_t ph = 0;
       bool ring_pass = false;
@@ -706,6 +707,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         const CUtensorMap* amap = &tm.a[src];
         int kb = it_begin * BK;
         const int nrow = n_tile * BN + static_cast<int>(pr) * B_ROWS;
+        if (need_wait) {
+          pdl_wait();
+          need_wait = false;
+          if (is_a && !(dbg & 64)) SDB_TR(3, clock64() - clk0);
+        }
         for (int it = it_begin; it < it_end; ++it) {
           if (ring_pass) mbar_wait(&empty_bar[s], ph ^ 1);   // (first pass over the ring: every slot is free)
           if (is_a) {
