@@ -1264,14 +1264,14 @@ __global__ void __launch_bounds__(CQ * 8) splitk_epilogue_kernel(const GemmArgs 
   constexpr int CB = CQ * 4;
   __shared__ float red[8][CB][2];
   pdl_launch_dependents();
-  pdl_wait();
   const int tx = threadIdx.x % CQ, ty = threadIdx.x / CQ;
   const int col = blockIdx.x * CB + tx * 4;
   const size_t plane = static_cast<size_t>(p.M) * p.N;
   float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
+  float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col < p.N && p.bias) bv = *reinterpret_cast<const float4*>(p.bias + col);   // weights: before the dependency wait
+  pdl_wait();
   if (col < p.N) {
-    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p.bias) bv = *reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int row = blockIdx.y * 32 + ty + 8 * i;

@@ -190,6 +190,8 @@ __global__ void __launch_bounds__(GN_THREADS)
   const int n = blockIdx.y;
   __shared__ float mean_s[64], rstd_s[64];
   pdl_launch_dependents();
+  // gamma / beta are weights: park them in the table before the dependency wait (one L2 round trip off the chain)
+  for (int c = threadIdx.x; c < C; c += GN_THREADS) gn_ab[c] = make_float2(__ldg(gamma + c), __ldg(beta + c));
   pdl_wait();
   if (cs0) {
     // per-tile partial {sum, sum of squares} per sg-channel entry, stored by the producing GEMM epilogues
@@ -229,10 +231,11 @@ __global__ void __launch_bounds__(GN_THREADS)
     rstd_s[threadIdx.x] = meanrstd[(static_cast<size_t>(n) * groups + threadIdx.x) * 2 + 1];
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += GN_THREADS) {
+  for (int c = threadIdx.x; c < C; c += GN_THREADS) {   // each thread rewrites the entries it parked above
     const int g = c / cpg;
-    const float a = rstd_s[g] * gamma[c];
-    gn_ab[c] = make_float2(a, fmaf(-mean_s[g], a, beta[c]));
+    const float2 gb = gn_ab[c];
+    const float a = rstd_s[g] * gb.x;
+    gn_ab[c] = make_float2(a, fmaf(-mean_s[g], a, gb.y));
   }
   __syncthreads();
   const int r0 = blockIdx.x * rows_per_block;
