@@ -243,6 +243,35 @@ int sdb_pointwise_small(const float* x, int64_t npix, int32_t cin, int32_t cout,
 int sdb_embed_tokens(const int64_t* ids, int32_t rows, int32_t n_ctx, int32_t dim, int32_t vocab, const float* tok,
                      const float* pos, float* out, sdb_stream_t stream);
 
+/* ---- post-processing of the decoded image: safety checker (scripts/txt2img.py:26-29, 88-95, 319) ----
+ * The reference delegates to third-party code: transformers' CLIPFeatureExtractor (PIL bicubic resize of the shorter
+ * side to 224, centre crop, 1/255, mean/std) and diffusers' StableDiffusionSafetyChecker (CLIP ViT-L/14 vision tower +
+ * projection, cosine distance to 17 concept and 3 special-care embeddings). The vision tower runs on sdb_gemm /
+ * sdb_attention / sdb_layernorm; these are the pieces around it. */
+/* One pass of PIL's 8-bit ImagingResample over interleaved [n_img, H, W, 3] images: horizontal (vertical = 0: lines =
+ * rows, in_size / out_size = widths) or vertical (vertical = 1: lines = columns, other_size_in = the row length W).
+ * bounds int32 [out_size, 2] = {first source index, tap count}, coefs int32 [out_size, ksize] = 22-bit fixed-point
+ * weights, both computed by the host exactly as PIL's precompute_coeffs / normalize_coeffs_8bpc. The source is uint8,
+ * or fp32 in [0, 1] converted as numpy_to_pil does ((x * 255).round()). */
+int sdb_resample_u8(const void* src_u8, const float* src_f32, int32_t n_img, int32_t lines, int32_t in_size,
+                    int32_t out_size, int32_t ksize, const int32_t* bounds, const int32_t* coefs, int32_t vertical,
+                    int32_t other_size_in, void* out_u8, sdb_stream_t stream);
+/* centre crop to size x size, x / 255, (x - mean) / std: uint8 [nb, h, w, 3] -> fp32 NCHW [nb, 3, size, size] */
+int sdb_clip_normalize(const void* img_u8, int32_t nb, int32_t h, int32_t w, int32_t size, float m0, float m1, float m2,
+                       float s0, float s1, float s2, float* out_nchw, sdb_stream_t stream);
+/* ViT patch extraction: NCHW fp32 [nb, 3, size, size] -> fp16 [nb * (size/patch)^2, kpad], k = (c * patch + py) * patch + px
+ * (the flattening of CLIPVisionEmbeddings.patch_embedding.weight), zero-padded to kpad (multiple of 64) */
+int sdb_patchify(const float* x_nchw, int32_t nb, int32_t size, int32_t patch, int32_t kpad, void* out_f16,
+                 sdb_stream_t stream);
+/* StableDiffusionSafetyChecker decision: scores fp32 [nb, n_special + n_concept] (rounded to 3 decimals as the
+ * library does), flagged int32 [nb] */
+int sdb_safety_scores(const float* image_embeds, int32_t nb, int32_t dim, const float* special_embeds,
+                      const float* special_weights, int32_t n_special, const float* concept_embeds,
+                      const float* concept_weights, int32_t n_concept, float* scores, int32_t* flagged,
+                      sdb_stream_t stream);
+/* images[i] = 0 for flagged images (fp32, per_image elements each) */
+int sdb_blank_flagged(float* images, int64_t per_image, int32_t nb, const int32_t* flagged, sdb_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Handle-level entry points: the engine, not just its kernels.
  *

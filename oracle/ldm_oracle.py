@@ -233,6 +233,94 @@ def get_first_stage_encoding(moments, noise, scale_factor=0.18215):
     return scale_factor * (mean + std * noise)
 
 
+# ----------------------------------------------------------------------------------------------- safety checker
+# scripts/txt2img.py:26-29, 88-95 delegate to third-party code absent from /root/reference: transformers'
+# CLIPFeatureExtractor + CLIPVisionModel (pinned 4.19.2 in environment.yaml:26) and diffusers'
+# StableDiffusionSafetyChecker (environment.yaml:30 diffusers, not installed here). The vision tower is pinned against
+# the installed transformers (tests/golden/safety.pt); the preprocessing calls PIL exactly as the extractor does; the
+# concept decision restates the published diffusers forward() - PARITY UNPINNED for that last step.
+def clip_image_preprocess(images, size=224, mean=(0.48145466, 0.4578275, 0.40821073),
+                          std=(0.26862954, 0.26130258, 0.27577711)):
+    """images: float [B, H, W, 3] in [0, 1] (x_samples_ddim of txt2img.py:316-319) -> pixel_values [B, 3, size, size].
+    numpy_to_pil ((x * 255).round() -> uint8), resize of the shorter side to `size` (PIL bicubic), centre crop,
+    1/255, normalise."""
+    import numpy as np
+    from PIL import Image
+    out = []
+    for img in images:
+        arr = (np.asarray(img, dtype=np.float32) * 255).round().astype("uint8")
+        pil = Image.fromarray(arr)
+        w, h = pil.size
+        short, long = (w, h) if w <= h else (h, w)
+        new_short, new_long = size, int(size * long / short)
+        nw, nh = (new_short, new_long) if w <= h else (new_long, new_short)
+        pil = pil.resize((nw, nh), resample=Image.BICUBIC)
+        left, top = (nw - size) // 2, (nh - size) // 2
+        pil = pil.crop((left, top, left + size, top + size))
+        a = np.asarray(pil).astype(np.float32) / 255.0
+        a = (a - np.asarray(mean, dtype=np.float32)) / np.asarray(std, dtype=np.float32)
+        out.append(torch.from_numpy(a).permute(2, 0, 1))
+    return torch.stack(out)
+
+
+def clip_vision_embeds(sd, pixel_values, num_heads, eps=1e-5, pre="vision_model.vision_model"):
+    """CLIPVisionModel pooled output -> visual_projection (StableDiffusionSafetyChecker.forward: image_embeds)."""
+    b = pixel_values.shape[0]
+    w = sd[f"{pre}.embeddings.patch_embedding.weight"]
+    h = w.shape[0]
+    patches = F.conv2d(pixel_values, w, stride=w.shape[-1]).flatten(2).transpose(1, 2)       # [b, n, h]
+    cls = sd[f"{pre}.embeddings.class_embedding"].expand(b, 1, h)
+    x = torch.cat([cls, patches], 1) + sd[f"{pre}.embeddings.position_embedding.weight"][None]
+    x = F.layer_norm(x, (h,), sd[f"{pre}.pre_layrnorm.weight"], sd[f"{pre}.pre_layrnorm.bias"], eps)
+    n = x.shape[1]
+    d = h // num_heads
+    i = 0
+    while f"{pre}.encoder.layers.{i}.layer_norm1.weight" in sd:
+        p = f"{pre}.encoder.layers.{i}"
+        r = x
+        y = F.layer_norm(x, (h,), sd[p + ".layer_norm1.weight"], sd[p + ".layer_norm1.bias"], eps)
+        q = F.linear(y, sd[p + ".self_attn.q_proj.weight"], sd[p + ".self_attn.q_proj.bias"]) * d ** -0.5
+        k = F.linear(y, sd[p + ".self_attn.k_proj.weight"], sd[p + ".self_attn.k_proj.bias"])
+        v = F.linear(y, sd[p + ".self_attn.v_proj.weight"], sd[p + ".self_attn.v_proj.bias"])
+        sp = lambda t: t.reshape(b, n, num_heads, d).permute(0, 2, 1, 3)
+        s = torch.matmul(sp(q), sp(k).transpose(-1, -2))
+        o = torch.matmul(s.softmax(-1), sp(v)).permute(0, 2, 1, 3).reshape(b, n, h)
+        x = r + F.linear(o, sd[p + ".self_attn.out_proj.weight"], sd[p + ".self_attn.out_proj.bias"])
+        r = x
+        y = F.layer_norm(x, (h,), sd[p + ".layer_norm2.weight"], sd[p + ".layer_norm2.bias"], eps)
+        y = F.linear(y, sd[p + ".mlp.fc1.weight"], sd[p + ".mlp.fc1.bias"])
+        y = y * torch.sigmoid(1.702 * y)
+        x = r + F.linear(y, sd[p + ".mlp.fc2.weight"], sd[p + ".mlp.fc2.bias"])
+        i += 1
+    pooled = F.layer_norm(x[:, 0], (h,), sd[f"{pre}.post_layernorm.weight"], sd[f"{pre}.post_layernorm.bias"], eps)
+    return F.linear(pooled, sd["visual_projection.weight"])
+
+
+def safety_decision(image_embeds, sd):
+    """The concept loop of StableDiffusionSafetyChecker.forward: (scores [B, n_special + n_concept], flagged [B])."""
+    def cos(a, b):
+        return F.normalize(a) @ F.normalize(b).t()
+    special = cos(image_embeds, sd["special_care_embeds"]).float().numpy()
+    concept = cos(image_embeds, sd["concept_embeds"]).float().numpy()
+    scores, flagged = [], []
+    for i in range(image_embeds.shape[0]):
+        adjustment = 0.0
+        row = []
+        for c in range(special.shape[1]):
+            sc = round(float(special[i][c]) - float(sd["special_care_embeds_weights"][c]) + adjustment, 3)
+            row.append(sc)
+            if sc > 0:
+                adjustment = 0.01
+        bad = False
+        for c in range(concept.shape[1]):
+            sc = round(float(concept[i][c]) - float(sd["concept_embeds_weights"][c]) + adjustment, 3)
+            row.append(sc)
+            bad = bad or sc > 0
+        scores.append(row)
+        flagged.append(bad)
+    return torch.tensor(scores), flagged
+
+
 # ----------------------------------------------------------------------------------------------- CLIP text
 def clip_text(sd, input_ids, num_heads, eps=1e-5):
     """CLIPTextModel(...).last_hidden_state as used by FrozenCLIPEmbedder.forward (modules.py:152-159):

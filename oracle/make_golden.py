@@ -26,7 +26,7 @@ import sdb200  # noqa: E402,F401
 from sdb200 import arch  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
-UNET_SEED, VAE_SEED, CLIP_SEED = 11, 12, 13
+UNET_SEED, VAE_SEED, CLIP_SEED, SAFETY_SEED = 11, 12, 13, 14
 
 
 def rel(a, b):
@@ -249,6 +249,39 @@ def clip_goldens():
     save("clip.pt", cases)
 
 
+def safety_goldens():
+    """Third-party arithmetic (CLIP vision tower + projection): pinned against the installed transformers
+    CLIPVisionModelWithProjection on random weights; preprocessing against PIL through the oracle."""
+    from transformers import CLIPVisionConfig, CLIPVisionModelWithProjection
+    cases = []
+    for tag, cfg in (("tiny", arch.TINY_SAFETY), ("sdv1", arch.SD_V1_SAFETY)):
+        hf_cfg = CLIPVisionConfig(hidden_size=cfg["hidden_size"], intermediate_size=cfg["intermediate_size"],
+                                  num_hidden_layers=cfg["num_hidden_layers"], num_attention_heads=cfg["num_attention_heads"],
+                                  image_size=cfg["image_size"], patch_size=cfg["patch_size"],
+                                  projection_dim=cfg["projection_dim"], hidden_act="quick_gelu",
+                                  layer_norm_eps=cfg["layer_norm_eps"])
+        model = CLIPVisionModelWithProjection(hf_cfg).eval()
+        sd = arch.random_state_dict(arch.safety_param_shapes(cfg), SAFETY_SEED)
+        hf_sd = {k[len("vision_model."):]: v for k, v in sd.items() if k.startswith("vision_model.")}
+        hf_sd["visual_projection.weight"] = sd["visual_projection.weight"]
+        missing, unexpected = model.load_state_dict(hf_sd, strict=False)
+        assert not unexpected and all("position_ids" in m for m in missing), (missing, unexpected)
+        g = torch.Generator().manual_seed(600)
+        # a smooth-ish random image in [0, 1] at twice the tower's input size, through the real preprocessing
+        img = torch.rand(2, cfg["image_size"] * 2 + 6, cfg["image_size"] * 2, 3, generator=g)
+        pix = O.clip_image_preprocess(img.numpy(), size=cfg["image_size"])
+        with torch.no_grad():
+            emb = model(pixel_values=pix).image_embeds
+        mine = O.clip_vision_embeds(sd, pix, cfg["num_attention_heads"], cfg["layer_norm_eps"])
+        print(f"safety {tag}: embeds std {float(emb.std()):.3f}; oracle rel {rel(mine, emb):.2e}")
+        cases.append(dict(cfg=tag, images=img if tag == "tiny" else None, pixel_values=pix.half() if tag != "tiny" else pix,
+                          image_embeds=emb, seed=SAFETY_SEED))   # (sdv1: fp16 pixels keep the fixture small; the
+        if tag != "tiny":                                          #  embeds below are those OF the rounded pixels)
+            with torch.no_grad():
+                cases[-1]["image_embeds"] = model(pixel_values=pix.half().float()).image_embeds
+    save("safety.pt", cases)
+
+
 def _sub(t, stride=4, off=1):
     """Strided pixel subset of an NCHW image (full-size decodes are megabytes; rel-L2 over a regular 1/16 sample of the
     pixels plus the whole-tensor norm pins the same arithmetic)."""
@@ -300,7 +333,7 @@ def fullsize_goldens():
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ["unet", "vae", "pipeline", "clip", "samplers_ext"]
+    which = sys.argv[1:] or ["unet", "vae", "pipeline", "clip", "samplers_ext", "safety"]
     if "unet" in which:
         unet_goldens()
     if "vae" in which:
@@ -309,6 +342,8 @@ if __name__ == "__main__":
         pipeline_goldens()
     if "clip" in which:
         clip_goldens()
+    if "safety" in which:
+        safety_goldens()
     if "samplers_ext" in which:
         samplers_ext_goldens()
     if "fullsize" in which:   # slow (minutes, ~20 GB of host memory): not part of the default set

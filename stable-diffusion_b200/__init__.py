@@ -7,9 +7,10 @@ __version__ = "0.1.0"
 
 import sys as _sys
 
-from . import arch, checkpoint, clip, diffusion, dist, lib, ops, pipeline, samplers, tokenizer, unet, util, vae  # noqa: E402,F401
+from . import arch, checkpoint, clip, diffusion, dist, lib, ops, pipeline, safety, samplers, tokenizer, unet, util, vae  # noqa: E402,F401
 from .clip import FrozenCLIPEmbedder  # noqa: E402,F401
 from .diffusion import LatentDiffusion  # noqa: E402,F401
+from .safety import StableDiffusionSafetyChecker  # noqa: E402,F401
 from .samplers import DDIMSampler, DPMSolverSampler, PLMSSampler  # noqa: E402,F401
 from .unet import UNetModel  # noqa: E402,F401
 from .vae import AutoencoderKL  # noqa: E402,F401

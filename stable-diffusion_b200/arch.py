@@ -23,6 +23,14 @@ SD_V1_VAE = dict(embed_dim=4, ddconfig=dict(double_z=True, z_channels=4, resolut
                                              dropout=0.0))
 SD_V1_CLIP = dict(vocab_size=49408, hidden_size=768, intermediate_size=3072, num_hidden_layers=12,
                   num_attention_heads=12, max_position_embeddings=77, layer_norm_eps=1e-5)
+# diffusers StableDiffusionSafetyChecker ("CompVis/stable-diffusion-safety-checker", scripts/txt2img.py:26-29): CLIP ViT-L/14
+# vision tower + projection, 17 concept and 3 special-care embeddings
+SD_V1_SAFETY = dict(hidden_size=1024, intermediate_size=4096, num_hidden_layers=24, num_attention_heads=16, image_size=224,
+                    patch_size=14, projection_dim=768, layer_norm_eps=1e-5, n_concepts=17, n_special=3)
+TINY_SAFETY = dict(hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2, image_size=56,
+                   patch_size=14, projection_dim=64, layer_norm_eps=1e-5, n_concepts=17, n_special=3)
+CLIP_IMAGE_MEAN = (0.48145466, 0.4578275, 0.40821073)
+CLIP_IMAGE_STD = (0.26862954, 0.26130258, 0.27577711)
 # small configs with the same topology, for fast CPU/GPU tests (head dims stay in the kernels' supported set)
 TINY_UNET = dict(image_size=16, in_channels=4, out_channels=4, model_channels=64, attention_resolutions=[2, 1],
                  num_res_blocks=1, channel_mult=[1, 2], num_heads=2, use_spatial_transformer=True,
@@ -276,11 +284,48 @@ def clip_param_shapes(cfg):
     return p
 
 
+def safety_param_shapes(cfg):
+    """Keys as diffusers StableDiffusionSafetyChecker.state_dict(): the CLIPVisionModel sits under `vision_model.`."""
+    h, inter, pd = cfg["hidden_size"], cfg["intermediate_size"], cfg["projection_dim"]
+    npos = (cfg["image_size"] // cfg["patch_size"]) ** 2 + 1
+    v = "vision_model.vision_model"
+    p = OrderedDict()
+    p[f"{v}.embeddings.class_embedding"] = (h,)
+    p[f"{v}.embeddings.patch_embedding.weight"] = (h, 3, cfg["patch_size"], cfg["patch_size"])
+    p[f"{v}.embeddings.position_embedding.weight"] = (npos, h)
+    p[f"{v}.pre_layrnorm.weight"] = (h,)
+    p[f"{v}.pre_layrnorm.bias"] = (h,)
+    for i in range(cfg["num_hidden_layers"]):
+        pre = f"{v}.encoder.layers.{i}"
+        for n in ("k_proj", "v_proj", "q_proj", "out_proj"):
+            p[f"{pre}.self_attn.{n}.weight"] = (h, h)
+            p[f"{pre}.self_attn.{n}.bias"] = (h,)
+        p[f"{pre}.layer_norm1.weight"] = (h,)
+        p[f"{pre}.layer_norm1.bias"] = (h,)
+        p[f"{pre}.mlp.fc1.weight"] = (inter, h)
+        p[f"{pre}.mlp.fc1.bias"] = (inter,)
+        p[f"{pre}.mlp.fc2.weight"] = (h, inter)
+        p[f"{pre}.mlp.fc2.bias"] = (h,)
+        p[f"{pre}.layer_norm2.weight"] = (h,)
+        p[f"{pre}.layer_norm2.bias"] = (h,)
+    p[f"{v}.post_layernorm.weight"] = (h,)
+    p[f"{v}.post_layernorm.bias"] = (h,)
+    p["visual_projection.weight"] = (pd, h)
+    p["concept_embeds"] = (cfg["n_concepts"], pd)
+    p["special_care_embeds"] = (cfg["n_special"], pd)
+    p["concept_embeds_weights"] = (cfg["n_concepts"],)
+    p["special_care_embeds_weights"] = (cfg["n_special"],)
+    return p
+
+
 # ------------------------------------------------------------------------------------------------ init
 def _is_norm_key(k):
     parts = k.split(".")
+    if len(parts) < 2:
+        return False
     leaf = parts[-2]
-    if leaf.startswith("norm") or leaf.startswith("layer_norm") or leaf in ("final_layer_norm", "norm_out"):
+    if leaf.startswith("norm") or leaf.startswith("layer_norm") or leaf in ("final_layer_norm", "norm_out", "pre_layrnorm",
+                                                                             "post_layernorm"):
         return True
     # UNet GroupNorms live at in_layers.0 / out_layers.0 / out.0
     return (len(parts) >= 3 and parts[-3] in ("in_layers", "out_layers") and leaf == "0") or k.startswith("out.0.")
@@ -299,6 +344,8 @@ def random_state_dict(shapes, seed, prefix="", device="cpu"):
         rn = lambda: torch.randn(shape, generator=g, device=device)
         if k.endswith(".bias"):
             t = 0.1 * rn()
+        elif k.endswith("_embeds_weights"):      # safety-checker thresholds
+            t = 0.15 + 0.05 * rn()
         elif _is_norm_key(k):
             t = 1.0 + 0.1 * rn()
         elif "embedding" in k:

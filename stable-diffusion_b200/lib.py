@@ -105,6 +105,12 @@ SIGNATURES = {
     "sdb_dpm_solver_step": ([_P, _P, _P, _I, _F, _F, _F, _I, _P, _F, _F, _F, _L, _P, _P, _P, _P], C.c_int),
     "sdb_mask_blend": ([_P, _P, _I, _I, _I, _L, _P, _P, _P], C.c_int),
     "sdb_axpby2": ([_P, _P, _F, _F, _L, _P, _P], C.c_int),
+    # post-processing (safety.cu)
+    "sdb_resample_u8": ([_P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P, _P], C.c_int),
+    "sdb_clip_normalize": ([_P, _I, _I, _I, _I, _F, _F, _F, _F, _F, _F, _P, _P], C.c_int),
+    "sdb_patchify": ([_P, _I, _I, _I, _I, _P, _P], C.c_int),
+    "sdb_safety_scores": ([_P, _I, _I, _P, _P, _I, _P, _P, _I, _P, _P, _P], C.c_int),
+    "sdb_blank_flagged": ([_P, _L, _I, _P, _P], C.c_int),
     # handle level (plan.cu)
     "sdb_plan_begin": ([C.POINTER(C.c_void_p)], C.c_int),
     "sdb_plan_end": ([_P], C.c_int),

@@ -549,9 +549,13 @@ def to_uint8(x):
     return out
 
 
-def axpby(x, a, b=0.0):
+def axpby(x, a, b=0.0, out=None):
     _chk32(x, "x")
-    out = torch.empty_like(x)
+    if out is None:
+        out = torch.empty_like(x)
+    else:
+        _chk32(out, "out")
+        assert out.numel() == x.numel()
     _l.check(_l.load().sdb_axpby(_ptr(x), a, b, x.numel(), _ptr(out), _stream()), "sdb_axpby")
     _count()
     return out

@@ -15,8 +15,10 @@ from sdb200 import arch  # noqa: E402
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 CFGS = {"unet": {"tiny": arch.TINY_UNET, "sdv1": arch.SD_V1_UNET},
         "vae": {"tiny": arch.TINY_VAE, "sdv1": arch.SD_V1_VAE},
-        "clip": {"tiny": arch.TINY_CLIP, "sdv1": arch.SD_V1_CLIP}}
-_SHAPES = {"unet": arch.unet_param_shapes, "vae": arch.vae_param_shapes, "clip": arch.clip_param_shapes}
+        "clip": {"tiny": arch.TINY_CLIP, "sdv1": arch.SD_V1_CLIP},
+        "safety": {"tiny": arch.TINY_SAFETY, "sdv1": arch.SD_V1_SAFETY}}
+_SHAPES = {"unet": arch.unet_param_shapes, "vae": arch.vae_param_shapes, "clip": arch.clip_param_shapes,
+           "safety": arch.safety_param_shapes}
 _cache = {}
 
 
