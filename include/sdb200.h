@@ -272,6 +272,13 @@ int sdb_safety_scores(const float* image_embeds, int32_t nb, int32_t dim, const 
 /* images[i] = 0 for flagged images (fp32, per_image elements each) */
 int sdb_blank_flagged(float* images, int64_t per_image, int32_t nb, const int32_t* flagged, sdb_stream_t stream);
 
+/* Invisible watermark of scripts/txt2img.py:69-74, 261-264, 324 (third-party `invisible-watermark`: WatermarkEncoder
+ * .encode(bgr, 'dwtDct') = EmbedMaxDct, scales [0, 36, 36], block 4) on uint8 RGB images [nb, h, w, 3]: cv2's 8-bit
+ * RGB -> YUV, one watermark bit per 4x4 block of the Haar approximation band of U, YUV -> RGB. bits: uint8 [n_bits]
+ * (0 / 1; "StableDiffusionV1" MSB first = 136 bits); yuv_scratch: nb*h*w*3 bytes. */
+int sdb_watermark_dwtdct(const void* rgb_u8, int32_t nb, int32_t h, int32_t w, const void* bits_u8, int32_t n_bits,
+                         float scale, void* yuv_scratch_u8, void* out_rgb_u8, sdb_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Handle-level entry points: the engine, not just its kernels.
  *

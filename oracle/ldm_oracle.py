@@ -321,6 +321,78 @@ def safety_decision(image_embeds, sd):
     return torch.tensor(scores), flagged
 
 
+# ----------------------------------------------------------------------------------------------- invisible watermark
+# scripts/txt2img.py:69-74, 261-264, 324 call the third-party `invisible-watermark` package (imwatermark 0.1.5 in
+# environment.yaml:28; absent from /root/reference and not installed here): WatermarkEncoder.set_watermark('bytes',
+# b"StableDiffusionV1") + encode(bgr, 'dwtDct') = EmbedMaxDct(scales=[0, 36, 36], block=4). Restated from the published
+# algorithm: BGR -> YUV (cv2, 8 bit), Haar DWT of the U plane (cropped to multiples of 4), in every 4x4 block of the
+# approximation band the largest-magnitude coefficient (excluding the first) is quantised to (floor(|v| / 36) + 0.25 +
+# 0.5 bit) * 36, inverse DWT written back into the uint8 plane (C truncation), YUV -> BGR. PARITY UNPINNED against the
+# package itself; the colour conversions are pinned against cv2 and the code is pinned by the decode round trip below.
+def watermark_bits(content=b"StableDiffusionV1"):
+    import numpy as np
+    return np.unpackbits(np.frombuffer(content, dtype=np.uint8)).astype(np.uint8)     # set_by_bytes: MSB first
+
+
+def _wm_block_positions(ca):
+    import numpy as np
+    r4, c4 = ca.shape[0] // 4, ca.shape[1] // 4
+    blocks = ca[: r4 * 4, : c4 * 4].reshape(r4, 4, c4, 4).transpose(0, 2, 1, 3).reshape(r4, c4, 16)
+    pos = np.argmax(np.abs(blocks[:, :, 1:]), axis=2) + 1
+    return blocks, pos, r4, c4
+
+
+def watermark_encode_dwtdct(rgb, bits=None, scale=36.0):
+    """rgb uint8 [H, W, 3] -> watermarked rgb uint8 (put_watermark, txt2img.py:69-74)."""
+    import cv2
+    import numpy as np
+    bits = watermark_bits() if bits is None else np.asarray(bits, dtype=np.uint8)
+    bgr = np.ascontiguousarray(rgb[:, :, ::-1])
+    row, col = bgr.shape[:2]
+    yuv = cv2.cvtColor(bgr, cv2.COLOR_BGR2YUV)
+    r, c = row // 4 * 4, col // 4 * 4
+    u = yuv[:r, :c, 1].astype(np.float64)
+    a, b, cc, d = u[0::2, 0::2], u[0::2, 1::2], u[1::2, 0::2], u[1::2, 1::2]
+    ca = (a + b + cc + d) / 2                     # Haar approximation band; the detail bands pass through unchanged
+    new = ca.copy()
+    blocks, pos, r4, c4 = _wm_block_positions(ca)
+    num = 0
+    for i in range(r4):
+        for j in range(c4):
+            p = int(pos[i, j])
+            v = blocks[i, j, p]
+            bit = float(bits[num % len(bits)])
+            q = (np.floor(abs(v) / scale) + 0.25 + 0.5 * bit) * scale
+            new[i * 4 + p // 4, j * 4 + p % 4] = q if v >= 0 else -q
+            num += 1
+    delta = (new - ca) / 2                        # inverse Haar: every pixel of the 2x2 cell moves by delta / 2 of its cA
+    up = u + np.repeat(np.repeat(delta, 2, axis=0), 2, axis=1)
+    yuv[:r, :c, 1] = up.astype(np.int64).astype(np.uint8)   # ndarray assignment float64 -> uint8: C truncation, mod 256
+    out = cv2.cvtColor(yuv, cv2.COLOR_YUV2BGR)
+    return np.ascontiguousarray(out[:, :, ::-1])
+
+
+def watermark_decode_dwtdct(rgb, n_bits=136, scale=36.0):
+    """EmbedMaxDct.decode: majority vote of (|v| mod scale > scale / 2) over the blocks that carry each bit."""
+    import cv2
+    import numpy as np
+    bgr = np.ascontiguousarray(rgb[:, :, ::-1])
+    row, col = bgr.shape[:2]
+    yuv = cv2.cvtColor(bgr, cv2.COLOR_BGR2YUV)
+    r, c = row // 4 * 4, col // 4 * 4
+    u = yuv[:r, :c, 1].astype(np.float64)
+    ca = (u[0::2, 0::2] + u[0::2, 1::2] + u[1::2, 0::2] + u[1::2, 1::2]) / 2
+    blocks, pos, r4, c4 = _wm_block_positions(ca)
+    votes = [[] for _ in range(n_bits)]
+    num = 0
+    for i in range(r4):
+        for j in range(c4):
+            v = abs(blocks[i, j, int(pos[i, j])])
+            votes[num % n_bits].append(1 if (v % scale) > 0.5 * scale else 0)
+            num += 1
+    return np.array([1 if sum(v) * 2 > len(v) else 0 for v in votes], dtype=np.uint8)
+
+
 # ----------------------------------------------------------------------------------------------- CLIP text
 def clip_text(sd, input_ids, num_heads, eps=1e-5):
     """CLIPTextModel(...).last_hidden_state as used by FrozenCLIPEmbedder.forward (modules.py:152-159):

@@ -150,6 +150,66 @@ __global__ void blank_flagged_kernel(float* __restrict__ img, size_t per_image, 
   }
 }
 
+// ---- invisible watermark (imwatermark EmbedMaxDct, method 'dwtDct', scales [0, 36, 36], block 4) ----
+// cv2's 8-bit BGR <-> YUV in its own 14-bit fixed point (checked exhaustively against cv2 in tests/test_safety_cpu.py)
+__device__ __forceinline__ int rs14(int x) { return (x + (1 << 13)) >> 14; }
+__global__ void wm_rgb2yuv_kernel(const uint8_t* __restrict__ rgb, size_t npix, uint8_t* __restrict__ yuv) {
+  SGRID_STRIDE(i, npix) {
+    const int r = rgb[3 * i], g = rgb[3 * i + 1], b = rgb[3 * i + 2];
+    const int y = rs14(b * 1868 + g * 9617 + r * 4899);
+    yuv[3 * i] = clip8(y);
+    yuv[3 * i + 1] = clip8(rs14((b - y) * 8061 + (128 << 14)));
+    yuv[3 * i + 2] = clip8(rs14((r - y) * 14369 + (128 << 14)));
+  }
+}
+__global__ void wm_yuv2rgb_kernel(const uint8_t* __restrict__ yuv, size_t npix, uint8_t* __restrict__ rgb) {
+  SGRID_STRIDE(i, npix) {
+    const int y = yuv[3 * i], u = yuv[3 * i + 1] - 128, v = yuv[3 * i + 2] - 128;
+    rgb[3 * i] = clip8(y + rs14(v * 18678));
+    rgb[3 * i + 1] = clip8(y + rs14(u * -6472 + v * -9519));
+    rgb[3 * i + 2] = clip8(y + rs14(u * 33292));
+  }
+}
+// One thread per 8x8 pixel block of the U plane = one 4x4 block of the Haar approximation band: quantise its
+// largest-magnitude coefficient (excluding the first) to carry one watermark bit; the inverse transform moves the four
+// pixels of that coefficient's 2x2 cell by delta / 2 and is written back with C truncation (float64 -> uint8).
+__global__ void wm_embed_kernel(uint8_t* __restrict__ yuv, int nb, int h, int w, const uint8_t* __restrict__ bits,
+                                int n_bits, double scale) {
+  const int r4 = (h / 4 * 4) / 8, c4 = (w / 4 * 4) / 8;
+  const size_t total = static_cast<size_t>(nb) * r4 * c4;
+  SGRID_STRIDE(t, total) {
+    const int j = static_cast<int>(t % c4);
+    const int i = static_cast<int>((t / c4) % r4);
+    const int b = static_cast<int>(t / (static_cast<size_t>(c4) * r4));
+    uint8_t* base = yuv + ((static_cast<size_t>(b) * h + 8 * i) * w + 8 * j) * 3 + 1;
+    const size_t rowp = static_cast<size_t>(w) * 3;
+    int best = 1;
+    double bestv = 0.0, bestabs = -1.0;
+    for (int k = 1; k < 16; ++k) {
+      const int cy = k >> 2, cx = k & 3;
+      const uint8_t* q = base + (2 * cy) * rowp + (2 * cx) * 3;
+      const double ca = (static_cast<double>(q[0]) + q[3] + q[rowp] + q[rowp + 3]) * 0.5;
+      if (fabs(ca) > bestabs) {   // np.argmax: first occurrence of the maximum
+        bestabs = fabs(ca);
+        bestv = ca;
+        best = k;
+      }
+    }
+    const int num = i * c4 + j;
+    const double bit = static_cast<double>(bits[num % n_bits]);
+    double qv = (floor(bestabs / scale) + 0.25 + 0.5 * bit) * scale;
+    if (bestv < 0.0) qv = -qv;
+    const double half_delta = (qv - bestv) * 0.5;
+    uint8_t* q = base + (2 * (best >> 2)) * rowp + (2 * (best & 3)) * 3;
+    for (int dy = 0; dy < 2; ++dy)
+      for (int dx = 0; dx < 2; ++dx) {
+        uint8_t* px = q + dy * rowp + dx * 3;
+        const double nv = static_cast<double>(*px) + half_delta;
+        *px = static_cast<uint8_t>(static_cast<long long>(nv) & 0xff);
+      }
+  }
+}
+
 }  // namespace sdb
 
 using namespace sdb;
@@ -230,6 +290,24 @@ extern "C" int sdb_blank_flagged(float* images, int64_t per_image, int32_t nb, c
   SDB_CHECK(images && flagged && per_image > 0 && nb > 0, "sdb_blank_flagged: bad arguments");
   blank_flagged_kernel<<<sgrid(static_cast<size_t>(per_image) * nb), 256, 0, ST>>>(images, static_cast<size_t>(per_image), nb,
                                                                                   flagged);
+  SDB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sdb_watermark_dwtdct(const void* rgb_u8, int32_t nb, int32_t h, int32_t w, const void* bits_u8, int32_t n_bits,
+                                    float scale, void* yuv_scratch_u8, void* out_rgb_u8, sdb_stream_t stream) {
+  SDB_REC(sdb_watermark_dwtdct(rgb_u8, nb, h, w, bits_u8, n_bits, scale, yuv_scratch_u8, out_rgb_u8, s_));
+  SDB_CHECK(rgb_u8 && bits_u8 && yuv_scratch_u8 && out_rgb_u8 && nb > 0 && n_bits > 0 && scale > 0.f,
+            "sdb_watermark_dwtdct: bad arguments");
+  SDB_CHECK(static_cast<long>(h) * w >= 256 * 256, "sdb_watermark_dwtdct: image too small (the encoder needs >= 256x256 pixels)");
+  const size_t npix = static_cast<size_t>(nb) * h * w;
+  wm_rgb2yuv_kernel<<<sgrid(npix), 256, 0, ST>>>(static_cast<const uint8_t*>(rgb_u8), npix, static_cast<uint8_t*>(yuv_scratch_u8));
+  SDB_LAUNCH_CHECK();
+  const size_t blocks = static_cast<size_t>(nb) * ((h / 4 * 4) / 8) * ((w / 4 * 4) / 8);
+  wm_embed_kernel<<<sgrid(blocks), 256, 0, ST>>>(static_cast<uint8_t*>(yuv_scratch_u8), nb, h, w,
+                                                 static_cast<const uint8_t*>(bits_u8), n_bits, static_cast<double>(scale));
+  SDB_LAUNCH_CHECK();
+  wm_yuv2rgb_kernel<<<sgrid(npix), 256, 0, ST>>>(static_cast<const uint8_t*>(yuv_scratch_u8), npix, static_cast<uint8_t*>(out_rgb_u8));
   SDB_LAUNCH_CHECK();
   return 0;
 }

@@ -111,6 +111,7 @@ SIGNATURES = {
     "sdb_patchify": ([_P, _I, _I, _I, _I, _P, _P], C.c_int),
     "sdb_safety_scores": ([_P, _I, _I, _P, _P, _I, _P, _P, _I, _P, _P, _P], C.c_int),
     "sdb_blank_flagged": ([_P, _L, _I, _P, _P], C.c_int),
+    "sdb_watermark_dwtdct": ([_P, _I, _I, _I, _P, _I, _F, _P, _P, _P], C.c_int),
     # handle level (plan.cu)
     "sdb_plan_begin": ([C.POINTER(C.c_void_p)], C.c_int),
     "sdb_plan_end": ([_P], C.c_int),

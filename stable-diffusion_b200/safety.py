@@ -267,3 +267,42 @@ class StableDiffusionSafetyChecker(nn.Module):
                 if bad and tuple(replacement.shape) == tuple(x_checked[i].shape):
                     x_checked[i].copy_(replacement)
         return x_checked, has
+
+
+class WatermarkEncoder:
+    """`imwatermark.WatermarkEncoder` as scripts/txt2img.py:261-264 uses it (`set_watermark('bytes', b"StableDiffusionV1")`,
+    `encode(img, 'dwtDct')`), on the GPU: uint8 RGB cuda tensors [H, W, 3] or [B, H, W, 3] in, watermarked uint8 RGB out
+    (the script's RGB -> BGR -> encode -> RGB round trip folded into the kernels)."""
+
+    def __init__(self):
+        self._bits = None
+
+    def set_watermark(self, wm_type="bytes", content=b""):
+        if wm_type != "bytes":
+            raise NotImplementedError("only the 'bytes' watermark of scripts/txt2img.py is implemented")
+        self._bits = np.unpackbits(np.frombuffer(bytes(content), dtype=np.uint8)).astype(np.uint8)
+        self._dev = {}
+
+    def encode(self, img, method="dwtDct"):
+        if method != "dwtDct":
+            raise NotImplementedError("only the 'dwtDct' method of scripts/txt2img.py is implemented")
+        if self._bits is None or len(self._bits) == 0:
+            raise RuntimeError("set_watermark() first")
+        if not (img.is_cuda and img.dtype == torch.uint8):
+            raise RuntimeError("sdb200.WatermarkEncoder takes uint8 CUDA tensors (no CPU fallback)")
+        single = img.dim() == 3
+        x = (img[None] if single else img).contiguous()
+        B, H, W, _ = x.shape
+        bits = self._dev.get(str(x.device))
+        if bits is None:
+            bits = self._dev[str(x.device)] = torch.from_numpy(self._bits).to(x.device)
+        scratch = torch.empty_like(x)
+        out = torch.empty_like(x)
+        _l.check(_l.load().sdb_watermark_dwtdct(_ptr(x), B, H, W, _ptr(bits), int(bits.numel()), 36.0, _ptr(scratch), _ptr(out),
+                                                _stream()), "sdb_watermark_dwtdct")
+        return out[0] if single else out
+
+
+def put_watermark(img, wm_encoder=None):
+    """scripts/txt2img.py:69-74 for uint8 RGB cuda tensors."""
+    return img if wm_encoder is None else wm_encoder.encode(img, "dwtDct")

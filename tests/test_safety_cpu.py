@@ -80,3 +80,35 @@ def test_product_module_has_no_cpu_path():
         chk.image_embeds(torch.zeros(1, 3, 56, 56))
     with pytest.raises(RuntimeError):
         chk.feature_extractor(torch.zeros(1, 8, 8, 3))
+
+
+def test_cv2_yuv_fixed_point_restatement():
+    """The kernels' BGR <-> YUV arithmetic (14-bit fixed point) equals cv2's 8-bit COLOR_BGR2YUV / COLOR_YUV2BGR."""
+    import cv2
+    rng = np.random.default_rng(0)
+    bgr = rng.integers(0, 256, size=(1 << 18, 1, 3), dtype=np.uint8)
+    yuv = cv2.cvtColor(bgr, cv2.COLOR_BGR2YUV).reshape(-1, 3).astype(np.int64)
+    B, G, R = [bgr.reshape(-1, 3)[:, i].astype(np.int64) for i in range(3)]
+    rs = lambda x: (x + (1 << 13)) >> 14
+    Y = rs(B * 1868 + G * 9617 + R * 4899)
+    assert np.array_equal(np.clip(Y, 0, 255), yuv[:, 0])
+    assert np.array_equal(np.clip(rs((B - Y) * 8061 + (128 << 14)), 0, 255), yuv[:, 1])
+    assert np.array_equal(np.clip(rs((R - Y) * 14369 + (128 << 14)), 0, 255), yuv[:, 2])
+    back = cv2.cvtColor(yuv.astype(np.uint8).reshape(-1, 1, 3), cv2.COLOR_YUV2BGR).reshape(-1, 3).astype(np.int64)
+    y, u, v = yuv[:, 0], yuv[:, 1] - 128, yuv[:, 2] - 128
+    assert np.array_equal(np.clip(y + rs(u * 33292), 0, 255), back[:, 0])
+    assert np.array_equal(np.clip(y + rs(u * -6472 + v * -9519), 0, 255), back[:, 1])
+    assert np.array_equal(np.clip(y + rs(v * 18678), 0, 255), back[:, 2])
+
+
+def test_watermark_oracle_round_trip():
+    """encode -> decode recovers b"StableDiffusionV1" (the property that pins the restated EmbedMaxDct)."""
+    import cv2
+    rng = np.random.default_rng(1)
+    for shape in ((512, 512), (300, 260), (257, 515)):
+        img = cv2.GaussianBlur(np.clip(rng.normal(128, 45, size=shape + (3,)), 0, 255).astype(np.uint8), (9, 9), 3)
+        out = O.watermark_encode_dwtdct(img)
+        assert out.shape == img.shape and out.dtype == np.uint8
+        assert np.abs(out.astype(int) - img.astype(int)).max() <= 40          # invisible: a few grey levels
+        bits = O.watermark_decode_dwtdct(out)
+        assert bytes(np.packbits(bits)) == b"StableDiffusionV1"

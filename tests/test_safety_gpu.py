@@ -78,3 +78,24 @@ def test_check_safety_end_to_end(cuda_dev):
     assert [bool(v) for v in ((ref_scores[:, cfg["n_special"]:] > 0) & margin[:, cfg["n_special"]:]).any(1)] == \
         [bool(v) for v in ((sc[:, cfg["n_special"]:] > 0) & margin[:, cfg["n_special"]:]).any(1)]
     assert len(has) == 3 and out.shape == x.shape
+
+
+@pytest.mark.parametrize("shape", [(1, 512, 512), (2, 300, 260), (1, 257, 515)])
+def test_watermark_kernel_vs_oracle_and_round_trip(cuda_dev, shape):
+    """sdb_watermark_dwtdct equals the oracle byte for byte, and the watermark decodes from the GPU output."""
+    import cv2
+    b, h, w = shape
+    rng = np.random.default_rng(h + w)
+    imgs = np.stack([cv2.GaussianBlur(np.clip(rng.normal(128, 45, size=(h, w, 3)), 0, 255).astype(np.uint8), (9, 9), 3)
+                     for _ in range(b)])
+    enc = sdb200.safety.WatermarkEncoder()
+    enc.set_watermark("bytes", b"StableDiffusionV1")
+    out = enc.encode(torch.from_numpy(imgs).to(cuda_dev), "dwtDct")
+    torch.cuda.synchronize()
+    out = out.cpu().numpy()
+    for i in range(b):
+        ref = O.watermark_encode_dwtdct(imgs[i])
+        assert np.array_equal(out[i], ref), int(np.abs(out[i].astype(int) - ref.astype(int)).max())
+        assert bytes(np.packbits(O.watermark_decode_dwtdct(out[i]))) == b"StableDiffusionV1"
+    single = sdb200.safety.put_watermark(torch.from_numpy(imgs[0]).to(cuda_dev), enc)
+    assert np.array_equal(single.cpu().numpy(), out[0])
