@@ -114,7 +114,8 @@ int sdb_gemm_plan(const sdb_gemm_desc* d, int32_t* out);
  *   k  : fp16 [batch, nkv, heads*dpad]   (row stride ldk)
  *   vt : fp16 [batch, heads*dpad, ldvt]  (V transposed: channel-major, nkv valid columns)
  *   out: fp16 [batch, nq, heads*d]       (row stride ldo; unpadded head dim d)
- * dpad in {64,128,192} (head dim zero-padded to a multiple of 64 by the projection weights).
+ * dpad in {64,128,192} (head dim zero-padded to a multiple of 64 by the projection weights: columns d .. dpad-1 of q / k
+ * and rows d .. dpad-1 of each head of vt MUST be zero - the kernels only issue the tensor-core steps that hold real columns).
  * scale multiplies q.k before softmax (applied after the dot product, attention.py:180).
  * causal != 0 masks kv index > q index (CLIP text encoder).
  */

@@ -122,7 +122,11 @@ __global__ void __launch_bounds__(192)
   } else if (warp == 1) {
     if (elect_one()) {
       constexpr uint32_t idesc_s = umma_idesc_f16(AQ, AKV);
-      constexpr uint32_t idesc_o = umma_idesc_f16(AQ, DPAD);
+      // head dimension d < DPAD: columns d .. DPAD-1 of Q / K and rows d .. DPAD-1 of V^T are zero padding. Only the
+      // 16-wide K steps that hold real columns are issued for S, and O is accumulated ceil16(d) columns wide: the
+      // tensor pipe (and the TMEM port it blocks for the softmax warps' loads) is busy d/DPAD of the time it was
+      const int ksteps = (p.d + 15) >> 4;
+      const uint32_t idesc_o = umma_idesc_f16(AQ, ksteps * 16);
       const uint32_t q_addr = smem_u32(q_s);
       auto issue_s = [&](int j) {
         const int s = j & 1;            // S accumulator buffer
@@ -132,6 +136,7 @@ __global__ void __launch_bounds__(192)
         const uint32_t k_addr = smem_u32(k_s + ks * K_BYTES);
 #pragma unroll
         for (int kk = 0; kk < DPAD / 16; ++kk) {
+          if (kk >= ksteps) break;
           uint64_t da = umma_desc_k128(q_addr + (kk >> 2) * (AQ * 128) + (kk & 3) * 32);
           uint64_t db = umma_desc_k128(k_addr + (kk >> 2) * (AKV * 128) + (kk & 3) * 32);
           umma_f16(tmem + s * AKV, da, db, idesc_s, kk > 0 ? 1u : 0u);
@@ -227,13 +232,15 @@ __global__ void __launch_bounds__(192)
       }
       float sm[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       const float neg_m = -m_used;
+      // P buffer s was read by PV(j-2): waited for before the exponentials, so that they, the packs and the shared
+      // stores are one basic block and interleave (see attention_split_kernel)
+      if (j >= 2) mbar_wait(&pv_done[s], ((j - 2) >> 1) & 1);
 #pragma unroll
       for (int c = 0; c < AKV; ++c) {
         t[c] = fast_exp2(fmaf(t[c], p.scale_log2, neg_m));
         sm[c & 7] += t[c];
       }
       l += ((sm[0] + sm[1]) + (sm[2] + sm[3])) + ((sm[4] + sm[5]) + (sm[6] + sm[7]));
-      if (j >= 2) mbar_wait(&pv_done[s], ((j - 2) >> 1) & 1);  // P buffer s was read by PV(j-2)
       uint8_t* prow = p_s + s * P_BYTES + r * 128;
 #pragma unroll
       for (int c16 = 0; c16 < 8; ++c16) {
@@ -392,7 +399,10 @@ __global__ void __launch_bounds__(SPLIT_THREADS, 2)
   } else if (warp == 1) {
     if (elect_one()) {
       constexpr uint32_t idesc_s = umma_idesc_f16(AQ, AKV);
-      constexpr uint32_t idesc_o = umma_idesc_f16(AQ, DPAD);
+      // d < 64: only the K steps holding real Q / K columns are issued, and the two output accumulators are
+      // ceil16(d + 1) columns wide (d value columns + the row-sum column d): d = 40 -> 3 of 4 K steps, N = 48 of 64
+      const int ksteps = (p.d + 15) >> 4;
+      const uint32_t idesc_o = umma_idesc_f16(AQ, min(DPAD, ((p.d + 16) >> 4) << 4));
       const uint32_t q_addr = smem_u32(q_s);
       auto issue_s = [&](int j) {
         const int s = j & 1;
@@ -402,6 +412,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS, 2)
         const uint32_t k_addr = smem_u32(k_s + ks * K_BYTES);
 #pragma unroll
         for (int kk = 0; kk < DPAD / 16; ++kk) {
+          if (kk >= ksteps) break;
           uint64_t da = umma_desc_k128(q_addr + kk * 32);
           uint64_t db = umma_desc_k128(k_addr + kk * 32);
           umma_f16(tmem + s * AKV, da, db, idesc_s, kk > 0 ? 1u : 0u);
@@ -489,9 +500,13 @@ __global__ void __launch_bounds__(SPLIT_THREADS, 2)
         if (need) m_used = m_new;
       }
       const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used;   // a fully masked half so far: exp2(-inf) = 0
+      // P buffer s was read by PV(j-2). Waited for BEFORE the exponentials (it completed long ago) so that scale /
+      // exponent / pack / store form one basic block: the packs and shared stores then issue between the MUFU
+      // instructions instead of after them (all softmax warps of an SM reach the MUFU phase together; whatever issues
+      // inside that phase is free)
+      if (j >= 2) mbar_wait(&pv_done[s], ((j - 2) >> 1) & 1);
 #pragma unroll
       for (int c = 0; c < 32; ++c) t[c] = fast_exp2(fmaf(t[c], p.scale_log2, neg_m));
-      if (j >= 2) mbar_wait(&pv_done[s], ((j - 2) >> 1) & 1);  // P buffer s was read by PV(j-2)
       uint8_t* prow = p_s + s * P_BYTES + r * 128;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
