@@ -1278,7 +1278,8 @@ __global__ void __launch_bounds__(CQ * 8) splitk_epilogue_kernel(const GemmArgs 
       if (row >= p.M) continue;
       const float* src = p.ws + static_cast<size_t>(row) * p.N + col;
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int sp = 0; sp < splits; ++sp) {
+#pragma unroll 4
+      for (int sp = 0; sp < splits; ++sp) {   // plane order: deterministic
         float4 t = __ldcg(reinterpret_cast<const float4*>(src + sp * plane));
         acc.x += t.x;
         acc.y += t.y;

@@ -437,9 +437,14 @@ extern "C" int sdb_gemm(const sdb_gemm_desc* d, sdb_stream_t stream) {
     const bool vec = (p.N % 4 == 0) && (p.ldo % 4 == 0) && (!p.residual || p.ldr % 4 == 0) && (!p.film || p.ldf % 4 == 0);
     if (vec) {
       const bool wide = p.N % 160 == 0 && 160 % p.stats_sg == 0;
-      const int cb = wide ? 160 : 128;
+      // small outputs (the 8x8 / 16x16 levels: 128 x 1280 -> 32 blocks of 160 columns, 12 planes summed by each
+      // thread: 10 us of pure latency on 32 SMs): 40-column blocks put four times as many SMs on the partial planes
+      const bool narrow = wide && 40 % p.stats_sg == 0 &&
+                          static_cast<long>(p.N / 160) * ((p.M + 31) / 32) < 2L * sm_count();
+      const int cb = narrow ? 40 : (wide ? 160 : 128);
       dim3 grid((p.N + cb - 1) / cb, (p.M + 31) / 32);
-      if (wide) SDB_CUDA(launch_pdl(splitk_epilogue_kernel<40>, grid, dim3(320), 0, st, p, splits));
+      if (narrow) SDB_CUDA(launch_pdl(splitk_epilogue_kernel<10>, grid, dim3(80), 0, st, p, splits));
+      else if (wide) SDB_CUDA(launch_pdl(splitk_epilogue_kernel<40>, grid, dim3(320), 0, st, p, splits));
       else SDB_CUDA(launch_pdl(splitk_epilogue_kernel<32>, grid, dim3(256), 0, st, p, splits));
     } else {
       SDB_CHECK(!p.stats, "sdb_gemm: stats_out with split-K needs n %% 4 == 0");
