@@ -16,11 +16,69 @@ import os
 import unicodedata
 
 try:
-    import regex as _re
-    _PAT = _re.compile(r"""'s|'t|'re|'ve|'m|'ll|'d|[\p{L}]+|[\p{N}]|[^\s\p{L}\p{N}]+""")
-except ImportError:   # stdlib approximation of \p{L} / \p{N}
-    import re as _re
-    _PAT = _re.compile(r"""'s|'t|'re|'ve|'m|'ll|'d|[^\W\d_]+|\d|(?:[^\s\w]|_)+""")
+    import regex as _regex
+    _PAT = _regex.compile(r"""'s|'t|'re|'ve|'m|'ll|'d|[\p{L}]+|[\p{N}]|[^\s\p{L}\p{N}]+""")
+except ImportError:   # the scanner below implements the same pattern with unicodedata (stdlib `re` has no \p{L} / \p{N}:
+    _regex = None     # its \d / [^\W\d_] approximations glue characters such as '²', '½', 'Ⅳ' to neighbouring words)
+    _PAT = None
+
+_CONTRACTIONS = ("'s", "'t", "'re", "'ve", "'m", "'ll", "'d")
+# \s of the `regex` / Rust regex engines = the Unicode White_Space property
+_WHITE = frozenset("\t\n\x0b\x0c\r \x85\xa0\u1680\u2000\u2001\u2002\u2003\u2004\u2005\u2006\u2007\u2008\u2009\u200a"
+                   "\u2028\u2029\u202f\u205f\u3000")
+
+
+def _is_letter(ch):
+    return unicodedata.category(ch)[0] == "L"
+
+
+def _is_number(ch):
+    return unicodedata.category(ch)[0] == "N"
+
+
+def split_clip(text):
+    """The CLIP pre-tokenisation pattern  's|'t|'re|'ve|'m|'ll|'d|[\\p{L}]+|[\\p{N}]|[^\\s\\p{L}\\p{N}]+  as a scanner over
+    Unicode general categories (leftmost match, alternatives tried in order, exactly as the regex does)."""
+    out, i, n = [], 0, len(text)
+    while i < n:
+        ch = text[i]
+        if ch == "'":
+            hit = next((c for c in _CONTRACTIONS if text.startswith(c, i)), None)
+            if hit:
+                out.append(hit)
+                i += len(hit)
+                continue
+        if _is_letter(ch):
+            j = i + 1
+            while j < n and _is_letter(text[j]):
+                j += 1
+        elif _is_number(ch):
+            j = i + 1
+        elif ch in _WHITE:
+            i += 1
+            continue
+        else:
+            j = i + 1
+            while j < n and not (text[j] in _WHITE or _is_letter(text[j]) or _is_number(text[j])):
+                j += 1
+        out.append(text[i:j])
+        i = j
+    return out
+
+
+def _collapse_white(text):
+    """Replace(Regex(r"\\s+"), " ") of the reference tokenizer's normaliser."""
+    out, prev = [], False
+    for ch in text:
+        if ch in _WHITE:
+            if not prev:
+                out.append(" ")
+            prev = True
+        else:
+            out.append(ch)
+            prev = False
+    return "".join(out)
+
 
 BOS, EOS = "<|startoftext|>", "<|endoftext|>"
 
@@ -93,10 +151,9 @@ class CLIPBPETokenizer:
         return word
 
     def _encode_plain(self, text):
-        text = unicodedata.normalize("NFC", text)
-        text = _re.sub(r"\s+", " ", text).lower()
+        text = _collapse_white(unicodedata.normalize("NFC", text)).lower()
         ids = []
-        for tok in _PAT.findall(text):
+        for tok in (_PAT.findall(text) if _PAT is not None else split_clip(text)):
             mapped = "".join(self.byte_encoder[b] for b in tok.encode("utf-8"))
             ids.extend(self.vocab.get(piece, self.unk_id) for piece in self._bpe(mapped))
         return ids

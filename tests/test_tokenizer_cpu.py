@@ -68,6 +68,12 @@ PROMPTS = [
     "x" * 40 + " " + "horse " * 120,                       # > 77 tokens: truncation keeps BOS + 75 + EOS
     "an astronaut <|endoftext|> riding <|startoftext|> a horse",
     "ＦＵＬＬ　ｗｉｄｔｈ and ﬁ ligature",
+    "x² + ½ cup, Ⅳ century, ③ items, 10⁻³ m",               # No / Nl number classes: single-character tokens
+    "東京タワー at night 夜景, 서울 skyline, москва зимой",       # CJK / Hangul / Cyrillic runs stay whole
+    "tab\there\x0bvertical\x0cform\x85next\u2028line\u3000wide\u00a0nbsp",     # every White_Space code point collapses
+    "zero\u200bwidth\ufeffbom\x00nul\x07bell\ufffdreplacement",           # Cf / Cc / U+FFFD are symbols, not spaces
+    "don't 'tis rock'n'roll o'clock 'LL 'Ve",
+    "e\u0301 vs \u00e9 (NFC), A\u030a, \u1e9b\u0323",
 ]
 
 
@@ -89,6 +95,25 @@ def test_matches_transformers_clip_tokenizer(toks):
         assert torch.equal(got[i], want[i]), (p, got[i].tolist()[:20], want[i].tolist()[:20])
     assert got[4].tolist() == [vocab[BOS]] + [vocab[EOS]] * 76            # empty prompt = the unconditional context
     assert int((got[7] != vocab[EOS]).sum()) == 76 and got[7, -1] == vocab[EOS]   # truncated to BOS + 75 tokens + EOS
+
+
+def test_stdlib_scanner_equals_the_regex_pattern():
+    """The unicodedata scanner (used when `regex` is not installed) splits exactly as the \\p{L} / \\p{N} pattern."""
+    regex = pytest.importorskip("regex")
+    from sdb200.tokenizer import _collapse_white, split_clip
+    pat = regex.compile(r"""'s|'t|'re|'ve|'m|'ll|'d|[\p{L}]+|[\p{N}]|[^\s\p{L}\p{N}]+""")
+    import random
+    import unicodedata
+    rng = random.Random(0)
+    pool = [chr(c) for c in list(range(0, 0x250)) + list(range(0x370, 0x400, 3)) + list(range(0x2000, 0x2070)) +
+            list(range(0x2150, 0x2190)) + list(range(0x2460, 0x2480)) + list(range(0x3000, 0x3100, 5)) +
+            list(range(0x4e00, 0x4e40)) + [0xfeff, 0xfffd, 0x1f680, 0x1d7ce, 0xac00]]
+    texts = list(PROMPTS) + ["".join(rng.choice(pool) for _ in range(60)) for _ in range(300)]
+    for tx in texts:
+        tx = unicodedata.normalize("NFC", tx)
+        assert _collapse_white(tx) == regex.sub(r"\s+", " ", tx), repr(tx)
+        low = _collapse_white(tx).lower()
+        assert split_clip(low) == pat.findall(low), repr(low)
 
 
 def test_loads_vocab_and_merges_files(toks, tmp_path):
