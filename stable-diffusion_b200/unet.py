@@ -448,7 +448,7 @@ class UNetModel(nn.Module):
         return ops.nhwc_to_nchw(o.view(nb, H, Wd, self.out_channels))
 
     def _graph_for(self, shape, kvs):
-        """Capture one UNet evaluation (~330 kernels) as a CUDA graph with static x / t / eps / K,V buffers."""
+        """Capture one UNet evaluation (~400 kernels) as a CUDA graph with static x / t / eps / K,V buffers."""
         g = self._graphs.get(shape)
         if g is None:
             dev = self.W["device"]
