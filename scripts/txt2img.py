@@ -4,8 +4,10 @@
   python scripts/txt2img.py --prompt "a photograph of an astronaut riding a horse" --plms --ckpt sd-v1-4.ckpt
 
 With --random_init the three stages get seeded random weights (no checkpoint ships offline); without the CLIP vocabulary
-files the prompt is replaced by seeded token ids (--token_seed). The safety checker and the invisible watermark of the
-reference script are third-party post-processing outside the denoising path and are not applied.
+files the prompt is replaced by seeded token ids (--token_seed). Post-processing as in the reference script
+(txt2img.py:317-327), on the GPU: the invisible watermark ("StableDiffusionV1", dwtDct) is always embedded unless
+--no_watermark; the safety checker runs when its weights are supplied (--safety_ckpt: a diffusers
+StableDiffusionSafetyChecker state dict, .safetensors or tensors-only pickle) - no weights ship offline.
 """
 import argparse
 import os
@@ -18,6 +20,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import sdb200  # noqa: E402
 from sdb200 import pipeline  # noqa: E402
+from sdb200.safety import StableDiffusionSafetyChecker, WatermarkEncoder, put_watermark  # noqa: E402
 
 DEFAULT_CONFIG = "configs/stable-diffusion/v1-inference.yaml"
 
@@ -79,6 +82,9 @@ def main():
     p.add_argument("--clip_vocab", type=str, default=None,
                    help="directory with the CLIP vocab.json + merges.txt (host-side BPE); default: transformers' local cache")
     p.add_argument("--token_seed", type=int, default=1234, help="seed of the stand-in token ids (no tokenizer offline)")
+    p.add_argument("--safety_ckpt", type=str, default=None,
+                   help="state dict of diffusers' StableDiffusionSafetyChecker: flagged images are blanked (txt2img.py:88-95)")
+    p.add_argument("--no_watermark", action="store_true", help="do not embed the invisible watermark (txt2img.py:261-264)")
     opt = p.parse_args()
     if opt.laion400m:
         raise NotImplementedError("--laion400m (a different checkpoint/config) is outside the SD-v1 path of this engine")
@@ -88,6 +94,17 @@ def main():
     sampler = "dpm_solver" if opt.dpm_solver else ("plms" if opt.plms else "ddim")
     pipe = pipeline.Txt2Img(model, sampler=sampler, steps=opt.ddim_steps, scale=opt.scale,
                             height=opt.H, width=opt.W, eta=opt.ddim_eta, f=opt.f, channels=opt.C)
+    safety_checker = None
+    if opt.safety_ckpt:
+        if not os.path.exists(opt.safety_ckpt):
+            raise FileNotFoundError(f"--safety_ckpt {opt.safety_ckpt} does not exist")
+        ssd, _ = sdb200.checkpoint.read_state_dict(opt.safety_ckpt, allow_pickle=opt.unsafe_ckpt)
+        safety_checker = StableDiffusionSafetyChecker().load_weights(ssd, device)
+    wm_encoder = None
+    if not opt.no_watermark:
+        print("Creating invisible watermark encoder (see https://github.com/ShieldMnt/invisible-watermark)...")
+        wm_encoder = WatermarkEncoder()
+        wm_encoder.set_watermark("bytes", "StableDiffusionV1".encode("utf-8"))
     os.makedirs(opt.outdir, exist_ok=True)
     sample_path = os.path.join(opt.outdir, "samples")
     os.makedirs(sample_path, exist_ok=True)
@@ -117,7 +134,15 @@ def main():
                 un[:, 0] = 49406
             x_T = start_code if start_code is not None else torch.randn(
                 [B, opt.C, opt.H // opt.f, opt.W // opt.f], device=device)      # plms.py:124
-            img = pipe(ids, un if opt.scale != 1.0 else None, x_T=x_T)           # uint8 [B, H, W, 3]
+            if safety_checker is not None:       # check_safety on the fp32 image, then 255 * x -> uint8 (txt2img.py:317-322)
+                x01 = pipe(ids, un if opt.scale != 1.0 else None, x_T=x_T, return_image01=True)
+                x01, has_nsfw = safety_checker.check_safety(x01)
+                if any(has_nsfw):
+                    print(f"safety checker: {sum(has_nsfw)} of {B} images blanked")
+                img = (255.0 * x01).to(torch.uint8)
+            else:
+                img = pipe(ids, un if opt.scale != 1.0 else None, x_T=x_T)       # uint8 [B, H, W, 3]
+            img = put_watermark(img, wm_encoder)                                 # txt2img.py:324
             n_img += B
             if not opt.skip_save:
                 from PIL import Image

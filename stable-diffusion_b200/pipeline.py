@@ -61,8 +61,9 @@ class Txt2Img:
         model.model.diffusion_model.use_cuda_graph = bool(cuda_graph)
 
     @torch.no_grad()
-    def __call__(self, ids, uncond_ids=None, x_T=None, return_latent=False):
-        """ids / uncond_ids: int64 [B, 77] (device). Returns uint8 [B, H, W, 3] on the device."""
+    def __call__(self, ids, uncond_ids=None, x_T=None, return_latent=False, return_image01=False):
+        """ids / uncond_ids: int64 [B, 77] (device). Returns uint8 [B, H, W, 3] on the device; return_image01=True
+        returns the fp32 image clamp((x + 1) / 2, 0, 1) instead (what txt2img.py:317-319 hands to check_safety)."""
         m = self.model
         B = ids.shape[0]
         if self.scale != 1.0:
@@ -77,6 +78,8 @@ class Txt2Img:
         if return_latent:
             return samples
         x = m.first_stage_model.decode(samples, scale=1. / m.scale_factor, nhwc=True)
+        if return_image01:
+            return torch.clamp((x + 1.0) / 2.0, min=0.0, max=1.0)
         return ops.to_uint8(x)
 
 
