@@ -329,6 +329,11 @@ def safety_decision(image_embeds, sd):
 # approximation band the largest-magnitude coefficient (excluding the first) is quantised to (floor(|v| / 36) + 0.25 +
 # 0.5 bit) * 36, inverse DWT written back into the uint8 plane (C truncation), YUV -> BGR. PARITY UNPINNED against the
 # package itself; the colour conversions are pinned against cv2 and the code is pinned by the decode round trip below.
+# Known open point (from memory of the published source, not checkable offline, NOT reproduced here or in the kernel): the
+# package's encode() is believed to hand the detail bands to pywt.idwt2 in swapped order, `(ca1, (v1, h1, d1))`, which for
+# the Haar wavelet exchanges the two off-diagonal pixels of every 2x2 cell of the U plane on top of the watermark delta
+# (the approximation band, and therefore what decode() reads, is unaffected). If that is what imwatermark 0.1.5 does, its
+# output differs from this restatement in those chroma pixels; the embedded bits and their decoding do not.
 def watermark_bits(content=b"StableDiffusionV1"):
     import numpy as np
     return np.unpackbits(np.frombuffer(content, dtype=np.uint8)).astype(np.uint8)     # set_by_bytes: MSB first
